@@ -1,0 +1,141 @@
+"""Weight dictionaries for the CRAFT detector and the CRNN recognizer.
+
+The product consumes weights in the reference's own naming so that the real
+checkpoints drop in unchanged:
+
+* CRAFT  -- the PyTorch state-dict keys of ``craft_mlt_25k.pth`` after the ``module.``
+  prefix is stripped (reference keras_ocr/detection.py:428-468 maps exactly these names
+  onto the Keras layers): ``<conv>.weight`` (O,I,kh,kw), ``<conv>.bias``,
+  ``<bn>.{weight,bias,running_mean,running_var}``.
+* CRNN   -- Keras layer names of ``build_model`` (reference recognition.py:214-329) with
+  Keras layouts: ``conv_N.kernel`` (kh,kw,I,O), ``bn_N.{gamma,beta,moving_mean,moving_variance}``,
+  ``lstm_N.{kernel,recurrent_kernel,bias}``, ``fc_N.{kernel,bias}``; the auto-named
+  localisation net is exposed as ``stn.conv_a / stn.conv_b / stn.dense_a / stn.dense_b``.
+
+No pretrained files exist offline, so ``synthetic_*`` build seeded weights with realistic
+statistics (He-scaled kernels, batch-norm statistics moved away from (0,1) so that folding
+mistakes show up in the parity tests).
+"""
+import numpy as np
+
+# name, cin, cout, kernel, dilation, batch-norm name (or None), relu after
+CRAFT_CONVS = [
+    ("basenet.slice1.0", 3, 64, 3, 1, "basenet.slice1.1", True),
+    ("basenet.slice1.3", 64, 64, 3, 1, "basenet.slice1.4", True),
+    ("basenet.slice1.7", 64, 128, 3, 1, "basenet.slice1.8", True),
+    ("basenet.slice1.10", 128, 128, 3, 1, "basenet.slice1.11", True),
+    ("basenet.slice2.14", 128, 256, 3, 1, "basenet.slice2.15", True),
+    ("basenet.slice2.17", 256, 256, 3, 1, "basenet.slice2.18", True),
+    ("basenet.slice3.20", 256, 256, 3, 1, "basenet.slice3.21", True),
+    ("basenet.slice3.24", 256, 512, 3, 1, "basenet.slice3.25", True),
+    ("basenet.slice3.27", 512, 512, 3, 1, "basenet.slice3.28", True),
+    ("basenet.slice4.30", 512, 512, 3, 1, "basenet.slice4.31", True),
+    ("basenet.slice4.34", 512, 512, 3, 1, "basenet.slice4.35", True),
+    ("basenet.slice4.37", 512, 512, 3, 1, "basenet.slice4.38", False),
+    ("basenet.slice5.1", 512, 1024, 3, 6, None, False),
+    ("basenet.slice5.2", 1024, 1024, 1, 1, None, False),
+    ("upconv1.conv.0", 1536, 512, 1, 1, "upconv1.conv.1", True),
+    ("upconv1.conv.3", 512, 256, 3, 1, "upconv1.conv.4", True),
+    ("upconv2.conv.0", 768, 256, 1, 1, "upconv2.conv.1", True),
+    ("upconv2.conv.3", 256, 128, 3, 1, "upconv2.conv.4", True),
+    ("upconv3.conv.0", 384, 128, 1, 1, "upconv3.conv.1", True),
+    ("upconv3.conv.3", 128, 64, 3, 1, "upconv3.conv.4", True),
+    ("upconv4.conv.0", 192, 64, 1, 1, "upconv4.conv.1", True),
+    ("upconv4.conv.3", 64, 32, 3, 1, "upconv4.conv.4", True),
+    ("conv_cls.0", 32, 32, 3, 1, None, True),
+    ("conv_cls.2", 32, 32, 3, 1, None, True),
+    ("conv_cls.4", 32, 16, 3, 1, None, True),
+    ("conv_cls.6", 16, 16, 1, 1, None, True),
+    ("conv_cls.8", 16, 2, 1, 1, None, False),
+]
+
+CRAFT_MAC_PER_PIXEL = 355720          # MAC per detector-input pixel
+CRAFT_FLOP_PER_PIXEL = 2 * CRAFT_MAC_PER_PIXEL
+CRNN_FLOP_PER_CROP = 13.444e9
+
+# name, cin, cout, kernel, batch-norm after the ReLU (or None)
+CRNN_CONVS = [
+    ("conv_1", 1, 64, 3, None),
+    ("conv_2", 64, 128, 3, None),
+    ("conv_3", 128, 256, 3, "bn_3"),
+    ("conv_4", 256, 256, 3, None),
+    ("conv_5", 256, 512, 3, "bn_5"),
+    ("conv_6", 512, 512, 3, None),
+    ("conv_7", 512, 512, 3, "bn_7"),
+]
+CRNN_LSTMS = ["lstm_10", "lstm_10_back", "lstm_11", "lstm_11_back"]
+ALPHABET = "0123456789abcdefghijklmnopqrstuvwxyz"     # reference recognition.py:25
+
+
+def _he(rng, shape, fan_in, gain=2.0):
+    return (rng.standard_normal(shape) * np.sqrt(gain / fan_in)).astype(np.float32)
+
+
+def synthetic_craft_weights(seed=0):
+    """Seeded CRAFT weights keyed like the reference's ``.pth`` (prefix stripped)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for name, cin, cout, k, _dil, bn, relu in CRAFT_CONVS:
+        gain = 2.0 if relu else 1.0
+        w[name + ".weight"] = _he(rng, (cout, cin, k, k), cin * k * k, gain)
+        w[name + ".bias"] = (rng.standard_normal(cout) * 0.05).astype(np.float32)
+        if bn is not None:
+            w[bn + ".weight"] = rng.uniform(0.8, 1.2, cout).astype(np.float32)
+            w[bn + ".bias"] = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+            w[bn + ".running_mean"] = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+            w[bn + ".running_var"] = rng.uniform(0.8, 1.25, cout).astype(np.float32)
+    return w
+
+
+def synthetic_crnn_weights(seed=1):
+    """Seeded CRNN weights keyed by Keras layer name (Keras layouts)."""
+    rng = np.random.default_rng(seed)
+    w = {}
+    for name, cin, cout, k, bn in CRNN_CONVS:
+        w[name + ".kernel"] = _he(rng, (k, k, cin, cout), cin * k * k)
+        w[name + ".bias"] = (rng.standard_normal(cout) * 0.05).astype(np.float32)
+        if bn is not None:
+            w[bn + ".gamma"] = rng.uniform(0.8, 1.2, cout).astype(np.float32)
+            w[bn + ".beta"] = (rng.standard_normal(cout) * 0.1).astype(np.float32)
+            w[bn + ".moving_mean"] = (rng.uniform(0.2, 0.6, cout)).astype(np.float32)
+            w[bn + ".moving_variance"] = rng.uniform(0.5, 1.2, cout).astype(np.float32)
+    w["stn.conv_a.kernel"] = _he(rng, (5, 5, 512, 16), 512 * 25)
+    w["stn.conv_a.bias"] = (rng.standard_normal(16) * 0.05).astype(np.float32)
+    w["stn.conv_b.kernel"] = _he(rng, (5, 5, 16, 32), 16 * 25)
+    w["stn.conv_b.bias"] = (rng.standard_normal(32) * 0.05).astype(np.float32)
+    w["stn.dense_a.kernel"] = _he(rng, (11200, 64), 11200)
+    w["stn.dense_a.bias"] = (rng.standard_normal(64) * 0.05).astype(np.float32)
+    # a trained STN sits near the identity transform [[1,0,0],[0,1,0]] with small deviations
+    w["stn.dense_b.kernel"] = (rng.standard_normal((64, 6)) * 0.01).astype(np.float32)
+    w["stn.dense_b.bias"] = (np.array([1, 0, 0, 0, 1, 0]) + rng.standard_normal(6) * 0.02).astype(np.float32)
+    w["fc_9.kernel"] = _he(rng, (3584, 128), 3584)
+    w["fc_9.bias"] = (rng.standard_normal(128) * 0.05).astype(np.float32)
+    for name in CRNN_LSTMS:
+        w[name + ".kernel"] = _he(rng, (128, 512), 128, 1.0)
+        w[name + ".recurrent_kernel"] = _he(rng, (128, 512), 128, 1.0)
+        b = (rng.standard_normal(512) * 0.05).astype(np.float32)
+        b[128:256] += 1.0                                   # unit_forget_bias
+        w[name + ".bias"] = b
+    w["fc_12.kernel"] = _he(rng, (256, len(ALPHABET) + 1), 256, 8.0)
+    w["fc_12.bias"] = (rng.standard_normal(len(ALPHABET) + 1) * 0.1).astype(np.float32)
+    return w
+
+
+def load_craft_pth(path):
+    """Read the reference's ``craft_mlt_25k.pth`` (sha256 in detection.py:647-652)."""
+    import torch
+
+    state = torch.load(path, map_location="cpu")
+    out = {}
+    for key, value in state.items():
+        if key.endswith("num_batches_tracked"):
+            continue
+        name = key[len("module."):] if key.startswith("module.") else key
+        out[name] = value.detach().cpu().numpy().astype(np.float32)
+    return out
+
+
+def load_npz(path):
+    """Weights exported to a flat ``.npz`` with the key names documented above."""
+    with np.load(path) as data:
+        return {k: data[k].astype(np.float32) for k in data.files}

@@ -1,0 +1,8 @@
+"""Import shim: the package sources live in ``keras-ocr_b200/`` (a directory name Python
+cannot import directly); this makes them importable as ``keras_ocr_b200``."""
+import os as _os
+
+_real = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "keras-ocr_b200")
+__path__ = [_real]
+with open(_os.path.join(_real, "__init__.py")) as _f:
+    exec(compile(_f.read(), _os.path.join(_real, "__init__.py"), "exec"))

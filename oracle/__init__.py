@@ -1,0 +1,28 @@
+"""CPU oracle for the keras-ocr ``Pipeline.recognize`` hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is imported by the product
+package (``keras-ocr_b200/``).  Only ``tests/``, ``__graft_entry__.smoke()`` and
+``bench.py``'s ``cpu_baseline`` / ``--impl reference`` legs may import it, and
+only as the checker / the CPU baseline.
+
+Every function restates one piece of the reference (``/root/reference``,
+faustomorales/keras-ocr @ 9661d6f) and cites the file:line it follows.  The
+restatement is validated in the authoring container against the reference's own
+code by ``oracle/validate_against_reference.py`` (which AST-lifts the reference
+functions at run time -- nothing is copied) and pinned by the fixtures that
+script writes to ``tests/golden/``.
+
+Pinning status ("Oracle"):
+
+* CRAFT graph            -- pinned: equals the reference's own PyTorch twin
+                            (detection.py:472-644) to 1e-5 on seeded weights.
+* getBoxes / warpBox /
+  resize / pad / inputs  -- pinned: equal to the lifted reference functions
+                            (same OpenCV 4.13) on the golden cases.
+* CRNN + STN + CTC       -- PARITY UNPINNED against TensorFlow: TensorFlow is
+                            not installable here, so the restatement follows
+                            the Keras semantics documented in SURVEY.md App. B.
+* shapely                -- absent; ``minimum_rotated_rectangle`` is restated
+                            as identity on 4-corner rectangles (the reference's
+                            own AttributeError fallback, tools.py:548-550).
+"""

@@ -1,0 +1,191 @@
+"""Pin the oracle against the reference itself and (re)generate ``tests/golden/``.
+
+Runs ONLY in the authoring container (needs /root/reference).  The reference package cannot
+be imported (TensorFlow, shapely, imgaug ... are absent), so individual functions are
+AST-lifted out of the reference sources *at run time* and executed with numpy / cv2 / scipy
+in scope.  Nothing is copied into this repository: the goldens hold inputs and the
+reference's outputs only.
+
+    python oracle/validate_against_reference.py            # check + write tests/golden/*.npz
+"""
+import ast
+import os
+import sys
+import types
+
+import cv2
+import numpy as np
+import torch
+from scipy import spatial
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+REF = os.environ.get("KERAS_OCR_REFERENCE", "/root/reference")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from oracle import craft as o_craft, imageops as o_img, synth  # noqa: E402
+from keras_ocr_b200 import weights as W  # noqa: E402
+
+
+def lift(path, names, scope):
+    """exec the named top-level functions of ``path`` inside ``scope``."""
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    missing = set(names) - {n.name for n in wanted}
+    assert not missing, missing
+    mod = ast.Module(body=wanted, type_ignores=[])
+    exec(compile(mod, path, "exec"), scope)
+    return scope
+
+
+class _NoShapely:
+    """Drives get_rotated_box down its own AttributeError branch (tools.py:548-550)."""
+
+    @staticmethod
+    def MultiPoint(points):
+        raise AttributeError("shapely absent")
+
+
+def reference_tools():
+    scope = {"np": np, "cv2": cv2, "spatial": spatial, "geometry": _NoShapely, "typing": __import__("typing"),
+             "tx": types.SimpleNamespace(Literal={"boxes": None, "predictions": None, "lines": None}.__class__),
+             "io": __import__("io"), "os": os}
+    # annotations in adjust_boxes reference tx.Literal[...]; strip annotations instead of stubbing
+    with open(os.path.join(REF, "keras_ocr", "tools.py")) as f:
+        tree = ast.parse(f.read())
+    names = {"get_rotated_width_height", "warpBox", "get_rotated_box", "pad", "resize_image", "adjust_boxes", "fix_line"}
+    body = []
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            node.returns = None
+            for a in node.args.args + node.args.kwonlyargs:
+                a.annotation = None
+            body.append(node)
+    exec(compile(ast.Module(body=body, type_ignores=[]), "tools.py", "exec"), scope)
+    return types.SimpleNamespace(**scope)
+
+
+def reference_detection(tools_ns):
+    scope = {"np": np, "cv2": cv2, "tools": tools_ns, "typing": __import__("typing")}
+    lift(os.path.join(REF, "keras_ocr", "detection.py"),
+         ["compute_input", "getBoxes", "get_gaussian_heatmap", "compute_maps", "build_torch_model"], scope)
+    return types.SimpleNamespace(**scope)
+
+
+def check_craft(det, out):
+    torch.manual_seed(0)
+    model = det.build_torch_model(None)
+    wts = W.synthetic_craft_weights(seed=3)
+    state = {k: torch.from_numpy(v) for k, v in wts.items()}
+    missing, unexpected = model.load_state_dict(state, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith("num_batches_tracked") or "slice4.40" in k or "slice4.41" in k for k in missing), missing
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for tag, (h, w) in {"even": (96, 128), "odd": (90, 114)}.items():
+        img = rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)
+        x = np.stack([det.compute_input(i) for i in img])
+        assert np.array_equal(x, np.stack([o_img.compute_input(i) for i in img]))
+        xt = torch.from_numpy(x).permute(0, 3, 1, 2).contiguous()
+        with torch.no_grad():
+            ref, _ = model(xt)
+            mine = o_craft.craft_forward(wts, xt)
+        err = float((ref - mine).abs().max())
+        worst = max(worst, err)
+        print(f"  CRAFT {tag} {h}x{w}: max|ref-oracle| = {err:.2e}  (out {tuple(ref.shape)})")
+        out[f"craft_{tag}_image"] = img
+        out[f"craft_{tag}_scores"] = ref.numpy()
+    assert worst < 1e-4, worst            # the reference's own Keras-vs-torch bar (tests/test_pytorch_keras.py:49)
+
+
+def check_boxes(det, out):
+    cases = {
+        "grid32": synth.score_maps(11, 2, 384, 384, 32),
+        "rot12": synth.score_maps(12, 2, 256, 320, 12),
+        "dense": synth.score_maps(13, 1, 200, 300, 60),
+        "blank": np.zeros((1, 64, 64, 2), np.float32),
+    }
+    # reference label generator as an extra, independent input (detection.py:55-62,106-198)
+    heat = det.get_gaussian_heatmap(size=128, distanceRatio=1.5)
+    lines = [[(np.array([[20 + 18 * i, 30], [36 + 18 * i, 30], [36 + 18 * i, 60], [20 + 18 * i, 60]], "float32"), "a")
+              for i in range(6)],
+             [(np.array([[60 + 22 * i, 150 + 4 * i], [80 + 22 * i, 154 + 4 * i], [76 + 22 * i, 190 + 4 * i], [56 + 22 * i, 186 + 4 * i]], "float32"), "b")
+              for i in range(5)]]
+    cases["refmaps"] = det.compute_maps(heat, 256, 320, lines)[np.newaxis].astype(np.float32)
+    for tag, maps in cases.items():
+        ref = det.getBoxes(maps)
+        mine = o_img.get_boxes(maps)
+        for r, m in zip(ref, mine):
+            assert r.shape == m.shape, (tag, r.shape, m.shape)
+            if r.size:
+                assert np.array_equal(r, m), (tag, np.abs(r - m).max())
+        counts = [len(r) for r in ref]
+        print(f"  getBoxes {tag}: boxes per image {counts} -- identical")
+        out[f"boxes_{tag}_scores"] = maps.astype(np.float32)
+        out[f"boxes_{tag}_counts"] = np.array(counts, np.int32)
+        flat = [r.reshape(-1, 4, 2) for r in ref if r.size]
+        out[f"boxes_{tag}_quads"] = np.concatenate(flat).astype(np.float32) if flat else np.zeros((0, 4, 2), np.float32)
+
+
+def check_warp(tools, out):
+    rng = np.random.default_rng(21)
+    gray = synth.noise_gray(rng, 480, 640)
+    quads = synth.random_quads(rng, 48, 480, 640)
+    crops = []
+    for q in quads:
+        ref = tools.warpBox(image=gray, box=q, target_height=31, target_width=200)
+        mine = o_img.warp_box(gray, q)
+        assert np.array_equal(ref, mine)
+        rb, _ = tools.get_rotated_box(q)
+        assert np.array_equal(rb, o_img.order_corners(q))
+        assert tools.get_rotated_width_height(rb) == o_img.rotated_width_height(rb)
+        crops.append(ref)
+    print(f"  warpBox: {len(quads)} quads identical")
+    out["warp_gray"] = gray
+    out["warp_quads"] = quads
+    out["warp_crops"] = np.stack(crops)
+
+
+def check_inputs(tools, out):
+    rng = np.random.default_rng(31)
+    for tag, (h, w, scale, max_size) in {"x2": (120, 160, 2, 2048), "capped": (300, 500, 2, 800), "x3": (77, 93, 3, 2048)}.items():
+        img = cv2.GaussianBlur(rng.integers(0, 256, (h, w, 3)).astype(np.float32), (0, 0), 1.2).clip(0, 255).astype(np.uint8)
+        ref, s_ref = tools.resize_image(img, max_scale=scale, max_size=max_size)
+        mine, s_mine = o_img.resize_image(img, scale, max_size)
+        assert s_ref == s_mine and np.array_equal(ref, mine)
+        rp = tools.pad(ref, width=ref.shape[1] + 7, height=ref.shape[0] + 3)
+        assert np.array_equal(rp, o_img.pad(mine, ref.shape[1] + 7, ref.shape[0] + 3))
+        gray = cv2.cvtColor(ref, code=cv2.COLOR_RGB2GRAY)
+        r64 = ref.astype(np.int64)
+        formula = ((9798 * r64[..., 0] + 19235 * r64[..., 1] + 3735 * r64[..., 2] + 16384) >> 15).astype(np.uint8)
+        assert np.array_equal(gray, formula)
+        out[f"resize_{tag}_src"] = img
+        out[f"resize_{tag}_dst"] = ref
+        out[f"resize_{tag}_params"] = np.array([scale, max_size, s_ref], np.float64)
+        print(f"  resize/pad/gray {tag}: {img.shape} -> {ref.shape} scale {s_ref:.4f} identical")
+    boxes = rng.uniform(0, 100, (5, 4, 2)).astype(np.float32)
+    assert np.array_equal(tools.adjust_boxes(boxes=boxes, boxes_format="boxes", scale=0.5), boxes * 0.5)
+
+
+def main():
+    assert os.path.isdir(REF), f"reference not found at {REF}"
+    os.makedirs(GOLDEN, exist_ok=True)
+    tools = reference_tools()
+    det = reference_detection(tools)
+    groups = {}
+    for name, fn, arg in [("craft", check_craft, det), ("boxes", check_boxes, det),
+                          ("warp", check_warp, tools), ("inputs", check_inputs, tools)]:
+        print(f"[{name}]")
+        out = {}
+        fn(arg, out)
+        groups[name] = out
+    for name, out in groups.items():
+        path = os.path.join(GOLDEN, f"{name}.npz")
+        np.savez_compressed(path, **out)
+        print(f"wrote {path} ({os.path.getsize(path) / 1e3:.0f} kB)")
+    print("oracle == reference on every case")
+
+
+if __name__ == "__main__":
+    main()
