@@ -1,0 +1,128 @@
+/*
+ * b2ocr.h -- C-ABI of the B200-native drop-in for keras_ocr.pipeline.Pipeline.recognize().
+ *
+ * The reference (faustomorales/keras-ocr @ 9661d6f) is pure Python and has no FFI of its own:
+ * its "device boundary" is two keras.Model.predict() calls (detection.py:779, recognition.py:535)
+ * plus OpenCV calls.  Each entry point below replaces one of those call sites; the reference
+ * line(s) it stands in for are cited.  INTEGRATION.md shows the ctypes binding a keras-ocr
+ * maintainer would add.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no torch / C++ types.  Every function returns 0 on success or a
+ *     negative b2o_status; b2o_last_error() gives the message.  No C++ exception crosses the ABI.
+ *   - "dev" pointers are CUDA device pointers on the context's device, "host" pointers are host
+ *     memory.  All work is enqueued on `stream` (a cudaStream_t passed as void*) and is
+ *     asynchronous unless stated.  The caller owns every I/O and workspace buffer; the library
+ *     owns only the packed weights inside the context.
+ *   - images are NHWC uint8 RGB; activations NHWC fp16; score maps NHWC fp32 (text, link).
+ *   - there is NO CPU fallback: without a CUDA device every call fails with B2O_ERR_CUDA.
+ */
+#ifndef B2OCR_H
+#define B2OCR_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2o_ctx b2o_ctx;
+
+typedef enum {
+  B2O_OK = 0,
+  B2O_ERR_CUDA = -1,       /* CUDA runtime / driver error (message has the detail)            */
+  B2O_ERR_ARG = -2,        /* bad argument (NULL, shape, alignment)                           */
+  B2O_ERR_WEIGHTS = -3,    /* missing / mis-shaped tensor in b2o_load_*                       */
+  B2O_ERR_WORKSPACE = -4,  /* workspace too small                                             */
+  B2O_ERR_STATE = -5       /* call needs weights that were not loaded                         */
+} b2o_status;
+
+/* One named float32 host tensor (row-major) of a checkpoint, in the reference's naming:
+ * CRAFT: PyTorch keys of craft_mlt_25k.pth without the "module." prefix (detection.py:428-468);
+ * CRNN : Keras layer names of build_model (recognition.py:214-329), Keras layouts.            */
+typedef struct {
+  const char* name;
+  const float* data;
+  int32_t ndim;
+  int64_t shape[4];
+} b2o_tensor;
+
+/* Which convolution engine to use: B2O_CONV_AUTO = tcgen05 wherever the shape allows (the product
+ * path), B2O_CONV_SIMT = CUDA-core debug engine used to cross-check the tcgen05 kernels.      */
+enum { B2O_CONV_AUTO = 0, B2O_CONV_SIMT = 1 };
+
+int b2o_version(void);
+int b2o_create(int device, b2o_ctx** out);
+void b2o_destroy(b2o_ctx* ctx);
+const char* b2o_last_error(const b2o_ctx* ctx);
+int b2o_set_conv_engine(b2o_ctx* ctx, int engine);
+/* number of kernels this library has launched since creation (bench.py's gpu_launches) */
+int64_t b2o_launch_count(const b2o_ctx* ctx);
+
+/* Detector() / Recognizer() weight loading (detection.py:686-696, recognition.py:382-404).
+ * Folds batch-norm, converts to fp16 and packs into the kernels' layouts on the device.      */
+int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n);
+int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n);
+
+/* tools.resize_image + tools.pad (tools.py:378-398, 356-375; pipeline.py:44-57), one image:
+ * bilinear (OpenCV fixed-point INTER_LINEAR) resize of src (hs x ws x 3) to (hr x wr), written into
+ * the top-left of dst image `index` of a (n, hp, wp, 3) batch; the rest is filled with 255.   */
+int b2o_resize_pad(b2o_ctx* ctx, const uint8_t* src_dev, int hs, int ws, int hr, int wr,
+                   uint8_t* dst_dev, int index, int hp, int wp, void* stream);
+
+/* cv2.cvtColor(RGB2GRAY) (recognition.py:510) for a whole (n,h,w,3) batch -> (n,h,w).         */
+int b2o_rgb_to_gray(b2o_ctx* ctx, const uint8_t* img_dev, int n, int h, int w, uint8_t* gray_dev,
+                    void* stream);
+
+/* compute_input + model.predict of Detector.detect (detection.py:34-42, 777-779): CRAFT forward.
+ * img: (n,h,w,3) uint8 RGB.  scores: (n, h/2, w/2, 2) float32.                                */
+size_t b2o_craft_workspace_bytes(int n, int h, int w);
+int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img_dev, int n, int h, int w, float* scores_dev,
+                      void* ws_dev, size_t ws_bytes, void* stream);
+
+/* getBoxes (detection.py:207-287).  scores: (n,hs,ws,2) float32.  Writes, per image i,
+ * counts[i] = number of boxes found (may exceed max_boxes: then only the first max_boxes are
+ * stored and the caller retries with a larger buffer) and boxes[i][k][4][2] float32 in
+ * detector-input pixels, in connected-component label order (= reference order).              */
+size_t b2o_boxes_workspace_bytes(int n, int hs, int ws, int max_boxes);
+int b2o_get_boxes(b2o_ctx* ctx, const float* scores_dev, int n, int hs, int ws,
+                  float detection_threshold, float text_threshold, float link_threshold,
+                  int size_threshold, float* boxes_dev, int32_t* counts_dev, int max_boxes,
+                  void* ws_dev, size_t ws_bytes, void* stream);
+
+/* tools.warpBox over box groups (recognition.py:506-519; tools.py:61-117).  boxes: (n_boxes,4,2)
+ * float32; image_index[k] selects the gray image of box k.  crops: (n_boxes,31,200) uint8
+ * (exactly warpBox's output) and, when crnn_in != NULL, the CRNN input (n_boxes,200,31) fp16 =
+ * crop/255 after Permute((2,1,3)) and the axis flip of recognition.py:215-216.                */
+int b2o_warp_boxes(b2o_ctx* ctx, const uint8_t* gray_dev, int n, int h, int w,
+                   const float* boxes_dev, const int32_t* image_index_dev, int n_boxes,
+                   uint8_t* crops_dev, void* crnn_in_dev, void* stream);
+
+/* prediction_model.predict (recognition.py:535; graph 214-333): CRNN + STN + BiLSTM + greedy CTC.
+ * crnn_in: (b,200,31) fp16 from b2o_warp_boxes (or b2o_crops_to_input).  labels: (b,48) int32,
+ * merged + blank-free, padded with -1 -- the tensor recognize_from_boxes iterates (527-534).  */
+size_t b2o_crnn_workspace_bytes(int b);
+int b2o_crops_to_input(b2o_ctx* ctx, const uint8_t* crops_dev, int b, void* crnn_in_dev, void* stream);
+int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in_dev, int b, int32_t* labels_dev,
+                     void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Debug / test taps (not on the product path): copy an intermediate of the last forward pass.
+ * b2o_crnn_tap names: "features" (b,50,7,512 f16), "theta" (b,6 f32), "warped" (b,50,7,512 f16),
+ * "fc_9" (b,50,128 f16), "l1" (b,50,128 f16), "l2" (b,50,256 f16), "logits" (b,48,37 f32).     */
+int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws_dev, int b, void* out_dev,
+                 size_t out_bytes, void* stream);
+
+/* One generic convolution through the selected engine (test hook for the conv kernels).
+ * x: (n,h,w,cin) fp16, wgt: (cout, k, k, cin) fp32 host, epilogue y = relu?(acc*s1+t1)*s2+t2.
+ * out: (n,h,w,cout) fp16.  s2/t2 may be NULL.                                                 */
+int b2o_conv2d_test(b2o_ctx* ctx, const void* x_dev, int n, int h, int w, int cin,
+                    const float* wgt_host, int cout, int ksize, int dilation,
+                    const float* s1_host, const float* t1_host, int relu,
+                    const float* s2_host, const float* t2_host, void* out_dev, int engine,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2OCR_H */

@@ -1,0 +1,529 @@
+// api.cu -- C-ABI entry points (include/b2ocr.h): context, weight packing, network orchestration.
+#include <math.h>
+#include <string.h>
+
+#include <functional>
+
+#include "common.cuh"
+
+int stn_theta_run(b2o_ctx* ctx, const __half* d1, int B, float* theta, cudaStream_t st);
+int stn_sample_run(b2o_ctx* ctx, const __half* feat, const float* theta, int B, __half* out, cudaStream_t st);
+int lstm_run(b2o_ctx* ctx, const float* xw, int xw_ld, int xw_off, const __half* u, int B, int backwards, __half* out,
+             int out_ld, int out_off, cudaStream_t st);
+int add_run(b2o_ctx* ctx, const __half* a, const __half* b, __half* o, long long n, cudaStream_t st);
+int fc_ctc_run(b2o_ctx* ctx, const __half* l2, int B, float* logits, int* labels, cudaStream_t st);
+
+namespace {
+
+typedef std::map<std::string, const b2o_tensor*> TensorMap;
+
+const b2o_tensor* need(b2o_ctx* ctx, const TensorMap& m, const std::string& name, int ndim, const int64_t* shape) {
+  auto it = m.find(name);
+  if (it == m.end()) { ctx->set_error("missing weight tensor: " + name); return nullptr; }
+  const b2o_tensor* t = it->second;
+  if (t->ndim != ndim) { ctx->set_error("bad rank for " + name); return nullptr; }
+  for (int i = 0; i < ndim; ++i)
+    if (t->shape[i] != shape[i]) { ctx->set_error("bad shape for " + name); return nullptr; }
+  return t;
+}
+
+template <typename T>
+T* dev_alloc(b2o_ctx* ctx, size_t count) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, count * sizeof(T)) != cudaSuccess) { ctx->set_error("cudaMalloc failed"); return nullptr; }
+  ctx->owned.push_back(p);
+  return reinterpret_cast<T*>(p);
+}
+
+template <typename T>
+T* dev_upload(b2o_ctx* ctx, const std::vector<T>& host) {
+  T* p = dev_alloc<T>(ctx, host.size());
+  if (!p) return nullptr;
+  if (cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice) != cudaSuccess) {
+    ctx->set_error("cudaMemcpy (weights) failed");
+    return nullptr;
+  }
+  return p;
+}
+
+// Build one layer.  wget(o, c, ky, kx) returns the fp32 weight.
+int build_layer(b2o_ctx* ctx, ConvLayer& L, const std::string& name, int cin, int cout, int ksize, int dil, int relu,
+                const std::function<float(int, int, int, int)>& wget, const std::vector<float>& s1,
+                const std::vector<float>& t1, const std::vector<float>* s2, const std::vector<float>* t2,
+                bool keep_f32_stem) {
+  L = ConvLayer();
+  L.name = name; L.cin = cin; L.cout = cout; L.ksize = ksize; L.dil = dil; L.relu = relu;
+  const int taps = ksize * ksize;
+  if (keep_f32_stem) {
+    std::vector<float> wf(static_cast<size_t>(taps) * cin * cout);
+    for (int ky = 0; ky < ksize; ++ky)
+      for (int kx = 0; kx < ksize; ++kx)
+        for (int c = 0; c < cin; ++c)
+          for (int o = 0; o < cout; ++o)
+            wf[(static_cast<size_t>(ky * ksize + kx) * cin + c) * cout + o] = wget(o, c, ky, kx);
+    if (!(L.w_f32 = dev_upload(ctx, wf))) return B2O_ERR_CUDA;
+  } else {
+    std::vector<__half> wk(static_cast<size_t>(cout) * taps * cin);
+    std::vector<float> ws(static_cast<size_t>(taps) * cin * cout);
+    for (int o = 0; o < cout; ++o)
+      for (int ky = 0; ky < ksize; ++ky)
+        for (int kx = 0; kx < ksize; ++kx)
+          for (int c = 0; c < cin; ++c) {
+            const __half hv = __float2half_rn(wget(o, c, ky, kx));
+            const int tap = ky * ksize + kx;
+            wk[(static_cast<size_t>(o) * taps + tap) * cin + c] = hv;
+            ws[(static_cast<size_t>(tap) * cin + c) * cout + o] = __half2float(hv);
+          }
+    if (!(L.w_kmajor = dev_upload(ctx, wk))) return B2O_ERR_CUDA;
+    if (!(L.w_simt = dev_upload(ctx, ws))) return B2O_ERR_CUDA;
+  }
+  if (!(L.s1 = dev_upload(ctx, s1))) return B2O_ERR_CUDA;
+  if (!(L.t1 = dev_upload(ctx, t1))) return B2O_ERR_CUDA;
+  if (s2) {
+    if (!(L.s2 = dev_upload(ctx, *s2))) return B2O_ERR_CUDA;
+    if (!(L.t2 = dev_upload(ctx, *t2))) return B2O_ERR_CUDA;
+  }
+  if (!keep_f32_stem) B2O_RETURN_IF(conv_tc_prepare(ctx, L));
+  return B2O_OK;
+}
+
+struct CraftSpec { const char* name; int cin, cout, k, dil; const char* bn; int relu; };
+const CraftSpec kCraft[] = {
+    {"basenet.slice1.0", 3, 64, 3, 1, "basenet.slice1.1", 1},     {"basenet.slice1.3", 64, 64, 3, 1, "basenet.slice1.4", 1},
+    {"basenet.slice1.7", 64, 128, 3, 1, "basenet.slice1.8", 1},   {"basenet.slice1.10", 128, 128, 3, 1, "basenet.slice1.11", 1},
+    {"basenet.slice2.14", 128, 256, 3, 1, "basenet.slice2.15", 1}, {"basenet.slice2.17", 256, 256, 3, 1, "basenet.slice2.18", 1},
+    {"basenet.slice3.20", 256, 256, 3, 1, "basenet.slice3.21", 1}, {"basenet.slice3.24", 256, 512, 3, 1, "basenet.slice3.25", 1},
+    {"basenet.slice3.27", 512, 512, 3, 1, "basenet.slice3.28", 1}, {"basenet.slice4.30", 512, 512, 3, 1, "basenet.slice4.31", 1},
+    {"basenet.slice4.34", 512, 512, 3, 1, "basenet.slice4.35", 1}, {"basenet.slice4.37", 512, 512, 3, 1, "basenet.slice4.38", 0},
+    {"basenet.slice5.1", 512, 1024, 3, 6, nullptr, 0},             {"basenet.slice5.2", 1024, 1024, 1, 1, nullptr, 0},
+    {"upconv1.conv.0", 1536, 512, 1, 1, "upconv1.conv.1", 1},      {"upconv1.conv.3", 512, 256, 3, 1, "upconv1.conv.4", 1},
+    {"upconv2.conv.0", 768, 256, 1, 1, "upconv2.conv.1", 1},       {"upconv2.conv.3", 256, 128, 3, 1, "upconv2.conv.4", 1},
+    {"upconv3.conv.0", 384, 128, 1, 1, "upconv3.conv.1", 1},       {"upconv3.conv.3", 128, 64, 3, 1, "upconv3.conv.4", 1},
+    {"upconv4.conv.0", 192, 64, 1, 1, "upconv4.conv.1", 1},        {"upconv4.conv.3", 64, 32, 3, 1, "upconv4.conv.4", 1},
+    {"conv_cls.0", 32, 32, 3, 1, nullptr, 1},                      {"conv_cls.2", 32, 32, 3, 1, nullptr, 1},
+    {"conv_cls.4", 32, 16, 3, 1, nullptr, 1},                      {"conv_cls.6", 16, 16, 1, 1, nullptr, 1},
+    {"conv_cls.8", 16, 2, 1, 1, nullptr, 0},
+};
+
+// Buffer plan of the CRAFT forward pass (all NHWC fp16 unless noted), carved from one workspace.
+struct CraftPlan {
+  int n, h1, w1, h2, w2, h4, w4, h8, w8, h16, w16;
+  size_t off_a, off_b, off_p1, off_c, off_cat4, off_p2, off_d, off_cat3, off_e, off_p3, off_f, off_cat2, off_g, off_p4,
+      off_hh, off_cat1, off_mp, off_s5a, off_u1a, off_u1b, off_u2a, off_u2b, off_u3a, off_u3b, off_u4a, off_u4b, off_h1,
+      off_h2, off_h3, bytes;
+};
+
+CraftPlan plan_craft(int n, int h, int w) {
+  CraftPlan p;
+  p.n = n; p.h1 = h; p.w1 = w;
+  p.h2 = h / 2; p.w2 = w / 2; p.h4 = p.h2 / 2; p.w4 = p.w2 / 2;
+  p.h8 = p.h4 / 2; p.w8 = p.w4 / 2; p.h16 = p.h8 / 2; p.w16 = p.w8 / 2;
+  size_t off = 0;
+  auto take = [&](int hh, int ww, int c) {
+    const size_t r = off;
+    off += (static_cast<size_t>(n) * hh * ww * c * 2 + 255) / 256 * 256;
+    return r;
+  };
+  p.off_a = take(p.h1, p.w1, 64); p.off_b = take(p.h1, p.w1, 64); p.off_p1 = take(p.h2, p.w2, 64);
+  p.off_c = take(p.h2, p.w2, 128); p.off_cat4 = take(p.h2, p.w2, 192); p.off_p2 = take(p.h4, p.w4, 128);
+  p.off_d = take(p.h4, p.w4, 256); p.off_cat3 = take(p.h4, p.w4, 384); p.off_e = take(p.h4, p.w4, 256);
+  p.off_p3 = take(p.h8, p.w8, 256); p.off_f = take(p.h8, p.w8, 512); p.off_cat2 = take(p.h8, p.w8, 768);
+  p.off_g = take(p.h8, p.w8, 512); p.off_p4 = take(p.h16, p.w16, 512); p.off_hh = take(p.h16, p.w16, 512);
+  p.off_cat1 = take(p.h16, p.w16, 1536); p.off_mp = take(p.h16, p.w16, 512); p.off_s5a = take(p.h16, p.w16, 1024);
+  p.off_u1a = take(p.h16, p.w16, 512); p.off_u1b = take(p.h16, p.w16, 256); p.off_u2a = take(p.h8, p.w8, 256);
+  p.off_u2b = take(p.h8, p.w8, 128); p.off_u3a = take(p.h4, p.w4, 128); p.off_u3b = take(p.h4, p.w4, 64);
+  p.off_u4a = take(p.h2, p.w2, 64); p.off_u4b = take(p.h2, p.w2, 32); p.off_h1 = take(p.h2, p.w2, 32);
+  p.off_h2 = take(p.h2, p.w2, 32); p.off_h3 = take(p.h2, p.w2, 16);
+  p.bytes = off;
+  return p;
+}
+
+struct CrnnPlan {
+  int b;
+  size_t off_x1, off_x2, off_x3, off_p3, off_x4, off_x5, off_p5, off_x6, off_x7, off_sa, off_sb, off_d1, off_theta,
+      off_warp, off_fc9, off_xw1, off_hf, off_hb, off_l1, off_xw2, off_l2, off_logits, bytes;
+};
+
+CrnnPlan plan_crnn(int b) {
+  CrnnPlan p;
+  p.b = b;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t r = off; off += (bytes + 255) / 256 * 256; return r; };
+  const size_t B = static_cast<size_t>(b);
+  p.off_x1 = take(B * 200 * 31 * 64 * 2); p.off_x2 = take(B * 200 * 31 * 128 * 2); p.off_x3 = take(B * 200 * 31 * 256 * 2);
+  p.off_p3 = take(B * 100 * 15 * 256 * 2); p.off_x4 = take(B * 100 * 15 * 256 * 2); p.off_x5 = take(B * 100 * 15 * 512 * 2);
+  p.off_p5 = take(B * 50 * 7 * 512 * 2); p.off_x6 = take(B * 50 * 7 * 512 * 2); p.off_x7 = take(B * 50 * 7 * 512 * 2);
+  p.off_sa = take(B * 50 * 7 * 16 * 2); p.off_sb = take(B * 50 * 7 * 32 * 2); p.off_d1 = take(B * 64 * 2);
+  p.off_theta = take(B * 6 * 4); p.off_warp = take(B * 50 * 7 * 512 * 2); p.off_fc9 = take(B * 50 * 128 * 2);
+  p.off_xw1 = take(B * 50 * 1024 * 4); p.off_hf = take(B * 50 * 128 * 2); p.off_hb = take(B * 50 * 128 * 2);
+  p.off_l1 = take(B * 50 * 128 * 2); p.off_xw2 = take(B * 50 * 1024 * 4); p.off_l2 = take(B * 50 * 256 * 2);
+  p.off_logits = take(B * 48 * 37 * 4);
+  p.bytes = off;
+  return p;
+}
+
+std::vector<float> ones(int n) { return std::vector<float>(static_cast<size_t>(n), 1.0f); }
+std::vector<float> tovec(const b2o_tensor* t, int n) { return std::vector<float>(t->data, t->data + n); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" int b2o_version(void) { return 1; }
+
+extern "C" int b2o_create(int device, b2o_ctx** out) {
+  if (!out) return B2O_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return B2O_ERR_CUDA;
+  if (cudaSetDevice(device) != cudaSuccess) return B2O_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2O_ERR_CUDA;
+  if (prop.major != 10) {
+    fprintf(stderr, "b2ocr: device %d is sm_%d%d; this library is built for sm_100a only\n", device, prop.major, prop.minor);
+    return B2O_ERR_CUDA;
+  }
+  b2o_ctx* ctx = new b2o_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  *out = ctx;
+  return B2O_OK;
+}
+
+extern "C" void b2o_destroy(b2o_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  for (void* p : ctx->owned) cudaFree(p);
+  delete ctx;
+}
+
+extern "C" const char* b2o_last_error(const b2o_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
+extern "C" int64_t b2o_launch_count(const b2o_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int b2o_set_conv_engine(b2o_ctx* ctx, int engine) {
+  if (!ctx || (engine != B2O_CONV_AUTO && engine != B2O_CONV_SIMT)) return B2O_ERR_ARG;
+  ctx->conv_engine = engine;
+  return B2O_OK;
+}
+
+extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
+  if (!ctx || !tensors) return B2O_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  TensorMap m;
+  for (int i = 0; i < n; ++i) m[tensors[i].name] = &tensors[i];
+  for (const CraftSpec& s : kCraft) {
+    const int64_t wshape[4] = {s.cout, s.cin, s.k, s.k};
+    const int64_t vshape[1] = {s.cout};
+    const b2o_tensor* w = need(ctx, m, std::string(s.name) + ".weight", 4, wshape);
+    const b2o_tensor* b = need(ctx, m, std::string(s.name) + ".bias", 1, vshape);
+    if (!w || !b) return B2O_ERR_WEIGHTS;
+    std::vector<float> s1 = ones(s.cout), t1 = tovec(b, s.cout);
+    if (s.bn) {
+      const b2o_tensor* g = need(ctx, m, std::string(s.bn) + ".weight", 1, vshape);
+      const b2o_tensor* be = need(ctx, m, std::string(s.bn) + ".bias", 1, vshape);
+      const b2o_tensor* mu = need(ctx, m, std::string(s.bn) + ".running_mean", 1, vshape);
+      const b2o_tensor* var = need(ctx, m, std::string(s.bn) + ".running_var", 1, vshape);
+      if (!g || !be || !mu || !var) return B2O_ERR_WEIGHTS;
+      for (int o = 0; o < s.cout; ++o) {      // BN(eps=1e-5) folded around the conv bias (detection.py:95-97)
+        const float sc = g->data[o] / sqrtf(var->data[o] + 1e-5f);
+        s1[o] = sc;
+        t1[o] = (b->data[o] - mu->data[o]) * sc + be->data[o];
+      }
+    }
+    const float* wd = w->data;
+    const int cin = s.cin, k = s.k;
+    auto wget = [wd, cin, k](int o, int c, int ky, int kx) { return wd[((static_cast<size_t>(o) * cin + c) * k + ky) * k + kx]; };
+    ConvLayer& L = ctx->craft[s.name];
+    B2O_RETURN_IF(build_layer(ctx, L, s.name, s.cin, s.cout, s.k, s.dil, s.relu, wget, s1, t1, nullptr, nullptr, s.cin == 3));
+  }
+  ctx->craft_loaded = true;
+  return B2O_OK;
+}
+
+extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
+  if (!ctx || !tensors) return B2O_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  TensorMap m;
+  for (int i = 0; i < n; ++i) m[tensors[i].name] = &tensors[i];
+  struct Spec { const char* name; int cin, cout, k; const char* bn; };
+  const Spec convs[] = {{"conv_1", 1, 64, 3, nullptr},    {"conv_2", 64, 128, 3, nullptr}, {"conv_3", 128, 256, 3, "bn_3"},
+                        {"conv_4", 256, 256, 3, nullptr}, {"conv_5", 256, 512, 3, "bn_5"}, {"conv_6", 512, 512, 3, nullptr},
+                        {"conv_7", 512, 512, 3, "bn_7"},  {"stn.conv_a", 512, 16, 5, nullptr}, {"stn.conv_b", 16, 32, 5, nullptr}};
+  for (const Spec& s : convs) {
+    const int64_t wshape[4] = {s.k, s.k, s.cin, s.cout};
+    const int64_t vshape[1] = {s.cout};
+    const b2o_tensor* w = need(ctx, m, std::string(s.name) + ".kernel", 4, wshape);
+    const b2o_tensor* b = need(ctx, m, std::string(s.name) + ".bias", 1, vshape);
+    if (!w || !b) return B2O_ERR_WEIGHTS;
+    std::vector<float> s1 = ones(s.cout), t1 = tovec(b, s.cout), s2, t2;
+    if (s.bn) {                                // BatchNormalization AFTER the ReLU, Keras eps = 1e-3
+      const b2o_tensor* g = need(ctx, m, std::string(s.bn) + ".gamma", 1, vshape);
+      const b2o_tensor* be = need(ctx, m, std::string(s.bn) + ".beta", 1, vshape);
+      const b2o_tensor* mu = need(ctx, m, std::string(s.bn) + ".moving_mean", 1, vshape);
+      const b2o_tensor* var = need(ctx, m, std::string(s.bn) + ".moving_variance", 1, vshape);
+      if (!g || !be || !mu || !var) return B2O_ERR_WEIGHTS;
+      s2.resize(s.cout); t2.resize(s.cout);
+      for (int o = 0; o < s.cout; ++o) {
+        const float sc = g->data[o] / sqrtf(var->data[o] + 1e-3f);
+        s2[o] = sc;
+        t2[o] = be->data[o] - mu->data[o] * sc;
+      }
+    }
+    const float* wd = w->data;
+    const int cin = s.cin, cout = s.cout, k = s.k;
+    auto wget = [wd, cin, cout, k](int o, int c, int ky, int kx) {
+      return wd[((static_cast<size_t>(ky) * k + kx) * cin + c) * cout + o];
+    };
+    ConvLayer& L = ctx->crnn[s.name];
+    B2O_RETURN_IF(build_layer(ctx, L, s.name, s.cin, s.cout, s.k, 1, 1, wget, s1, t1, s.bn ? &s2 : nullptr,
+                              s.bn ? &t2 : nullptr, s.cin == 1));
+  }
+  // dense layers as 1x1 "convolutions" over a (1,1,rows,K) view
+  struct Dense { const char* name; int k, n, relu; };
+  const Dense dense[] = {{"stn.dense_a", 11200, 64, 1}, {"fc_9", 3584, 128, 1}};
+  for (const Dense& d : dense) {
+    const int64_t wshape[2] = {d.k, d.n};
+    const int64_t vshape[1] = {d.n};
+    const b2o_tensor* w = need(ctx, m, std::string(d.name) + ".kernel", 2, wshape);
+    const b2o_tensor* b = need(ctx, m, std::string(d.name) + ".bias", 1, vshape);
+    if (!w || !b) return B2O_ERR_WEIGHTS;
+    const float* wd = w->data;
+    const int nn = d.n;
+    auto wget = [wd, nn](int o, int c, int, int) { return wd[static_cast<size_t>(c) * nn + o]; };
+    ConvLayer& L = ctx->crnn[d.name];
+    B2O_RETURN_IF(build_layer(ctx, L, d.name, d.k, d.n, 1, 1, d.relu, wget, ones(d.n), tovec(b, d.n), nullptr, nullptr, false));
+  }
+  {
+    const int64_t wshape[2] = {64, 6};
+    const int64_t vshape[1] = {6};
+    const b2o_tensor* w = need(ctx, m, "stn.dense_b.kernel", 2, wshape);
+    const b2o_tensor* b = need(ctx, m, "stn.dense_b.bias", 1, vshape);
+    if (!w || !b) return B2O_ERR_WEIGHTS;
+    if (!(ctx->stn_d2_w = dev_upload(ctx, tovec(w, 64 * 6)))) return B2O_ERR_CUDA;
+    if (!(ctx->stn_d2_b = dev_upload(ctx, tovec(b, 6)))) return B2O_ERR_CUDA;
+  }
+  // LSTM input projections: forward and go_backwards kernels side by side -> one GEMM per layer
+  const char* lstm_names[4] = {"lstm_10", "lstm_10_back", "lstm_11", "lstm_11_back"};
+  for (int layer = 0; layer < 2; ++layer) {
+    const int64_t wshape[2] = {128, 512};
+    const int64_t vshape[1] = {512};
+    const b2o_tensor* wf = need(ctx, m, std::string(lstm_names[2 * layer]) + ".kernel", 2, wshape);
+    const b2o_tensor* wb = need(ctx, m, std::string(lstm_names[2 * layer + 1]) + ".kernel", 2, wshape);
+    const b2o_tensor* bf = need(ctx, m, std::string(lstm_names[2 * layer]) + ".bias", 1, vshape);
+    const b2o_tensor* bb = need(ctx, m, std::string(lstm_names[2 * layer + 1]) + ".bias", 1, vshape);
+    if (!wf || !wb || !bf || !bb) return B2O_ERR_WEIGHTS;
+    const float* f = wf->data;
+    const float* bk = wb->data;
+    auto wget = [f, bk](int o, int c, int, int) { return o < 512 ? f[c * 512 + o] : bk[c * 512 + (o - 512)]; };
+    std::vector<float> bias(1024);
+    for (int i = 0; i < 512; ++i) { bias[i] = bf->data[i]; bias[512 + i] = bb->data[i]; }
+    const std::string lname = layer == 0 ? "lstm_in_1" : "lstm_in_2";
+    ConvLayer& L = ctx->crnn[lname];
+    B2O_RETURN_IF(build_layer(ctx, L, lname, 128, 1024, 1, 1, 0, wget, ones(1024), bias, nullptr, nullptr, false));
+    for (int dir = 0; dir < 2; ++dir) {
+      const b2o_tensor* u = need(ctx, m, std::string(lstm_names[2 * layer + dir]) + ".recurrent_kernel", 2, wshape);
+      if (!u) return B2O_ERR_WEIGHTS;
+      std::vector<__half> uh(128 * 512);
+      for (int i = 0; i < 128 * 512; ++i) uh[i] = __float2half_rn(u->data[i]);
+      if (!(ctx->lstm_u[2 * layer + dir] = dev_upload(ctx, uh))) return B2O_ERR_CUDA;
+    }
+  }
+  {
+    const int64_t wshape[2] = {256, 37};
+    const int64_t vshape[1] = {37};
+    const b2o_tensor* w = need(ctx, m, "fc_12.kernel", 2, wshape);
+    const b2o_tensor* b = need(ctx, m, "fc_12.bias", 1, vshape);
+    if (!w || !b) return B2O_ERR_WEIGHTS;
+    if (!(ctx->fc12_w = dev_upload(ctx, tovec(w, 256 * 37)))) return B2O_ERR_CUDA;
+    if (!(ctx->fc12_b = dev_upload(ctx, tovec(b, 37)))) return B2O_ERR_CUDA;
+  }
+  ctx->crnn_loaded = true;
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t b2o_craft_workspace_bytes(int n, int h, int w) {
+  if (n <= 0 || h < 32 || w < 32) return 0;
+  return plan_craft(n, h, w).bytes;
+}
+
+extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, float* scores, void* ws,
+                                 size_t ws_bytes, void* stream) {
+  if (!ctx) return B2O_ERR_ARG;
+  if (!ctx->craft_loaded) { ctx->set_error("b2o_craft_forward: CRAFT weights not loaded"); return B2O_ERR_STATE; }
+  if (!img || !scores || !ws || n <= 0 || h < 32 || w < 32) { ctx->set_error("b2o_craft_forward: bad argument"); return B2O_ERR_ARG; }
+  const CraftPlan p = plan_craft(n, h, w);
+  if (ws_bytes < p.bytes) { ctx->set_error("b2o_craft_forward: workspace too small"); return B2O_ERR_WORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  auto V = [&](size_t off, int hh, int ww, int c, int ld = 0, int coff = 0) { return make_view(base + off, n, hh, ww, c, ld, coff); };
+  auto L = [&](const char* name) -> const ConvLayer& { return ctx->craft[name]; };
+
+  const TensorView a = V(p.off_a, p.h1, p.w1, 64), b = V(p.off_b, p.h1, p.w1, 64), p1 = V(p.off_p1, p.h2, p.w2, 64);
+  const TensorView c = V(p.off_c, p.h2, p.w2, 128);
+  const TensorView cat4 = V(p.off_cat4, p.h2, p.w2, 192), cat4_y = V(p.off_cat4, p.h2, p.w2, 64, 192, 0),
+                   s1 = V(p.off_cat4, p.h2, p.w2, 128, 192, 64);
+  const TensorView p2 = V(p.off_p2, p.h4, p.w4, 128), d = V(p.off_d, p.h4, p.w4, 256);
+  const TensorView cat3 = V(p.off_cat3, p.h4, p.w4, 384), cat3_y = V(p.off_cat3, p.h4, p.w4, 128, 384, 0),
+                   s2 = V(p.off_cat3, p.h4, p.w4, 256, 384, 128);
+  const TensorView e = V(p.off_e, p.h4, p.w4, 256), p3 = V(p.off_p3, p.h8, p.w8, 256), f = V(p.off_f, p.h8, p.w8, 512);
+  const TensorView cat2 = V(p.off_cat2, p.h8, p.w8, 768), cat2_y = V(p.off_cat2, p.h8, p.w8, 256, 768, 0),
+                   s3 = V(p.off_cat2, p.h8, p.w8, 512, 768, 256);
+  const TensorView g = V(p.off_g, p.h8, p.w8, 512), p4 = V(p.off_p4, p.h16, p.w16, 512), hh = V(p.off_hh, p.h16, p.w16, 512);
+  const TensorView cat1 = V(p.off_cat1, p.h16, p.w16, 1536), s5 = V(p.off_cat1, p.h16, p.w16, 1024, 1536, 0),
+                   s4 = V(p.off_cat1, p.h16, p.w16, 512, 1536, 1024);
+  const TensorView mp = V(p.off_mp, p.h16, p.w16, 512), s5a = V(p.off_s5a, p.h16, p.w16, 1024);
+  const TensorView u1a = V(p.off_u1a, p.h16, p.w16, 512), u1b = V(p.off_u1b, p.h16, p.w16, 256);
+  const TensorView u2a = V(p.off_u2a, p.h8, p.w8, 256), u2b = V(p.off_u2b, p.h8, p.w8, 128);
+  const TensorView u3a = V(p.off_u3a, p.h4, p.w4, 128), u3b = V(p.off_u3b, p.h4, p.w4, 64);
+  const TensorView u4a = V(p.off_u4a, p.h2, p.w2, 64), u4b = V(p.off_u4b, p.h2, p.w2, 32);
+  const TensorView h1 = V(p.off_h1, p.h2, p.w2, 32), h2 = V(p.off_h2, p.h2, p.w2, 32), h3 = V(p.off_h3, p.h2, p.w2, 16);
+
+  // encoder (detection.py:312-324); taps s1..s4 are written straight into the concat buffers
+  B2O_RETURN_IF(stem_rgb_run(ctx, L("basenet.slice1.0"), img, n, h, w, a, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.3"), a, b, 0, st));
+  B2O_RETURN_IF(maxpool2_run(ctx, b, p1, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.7"), p1, c, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.10"), c, s1, 0, st));
+  B2O_RETURN_IF(maxpool2_run(ctx, s1, p2, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice2.14"), p2, d, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice2.17"), d, s2, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice3.20"), s2, e, 0, st));
+  B2O_RETURN_IF(maxpool2_run(ctx, e, p3, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice3.24"), p3, f, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice3.27"), f, s3, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice4.30"), s3, g, 0, st));
+  B2O_RETURN_IF(maxpool2_run(ctx, g, p4, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice4.34"), p4, hh, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice4.37"), hh, s4, 0, st));          // BN only, no ReLU (333)
+  // slice5 (365-378)
+  B2O_RETURN_IF(maxpool3s1_run(ctx, s4, mp, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice5.1"), mp, s5a, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice5.2"), s5a, s5, 0, st));
+  // decoder (380-390)
+  B2O_RETURN_IF(conv_run(ctx, L("upconv1.conv.0"), cat1, u1a, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("upconv1.conv.3"), u1a, u1b, 0, st));
+  B2O_RETURN_IF(upsample_run(ctx, u1b, cat2_y, st));
+  B2O_RETURN_IF(conv_run(ctx, L("upconv2.conv.0"), cat2, u2a, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("upconv2.conv.3"), u2a, u2b, 0, st));
+  B2O_RETURN_IF(upsample_run(ctx, u2b, cat3_y, st));
+  B2O_RETURN_IF(conv_run(ctx, L("upconv3.conv.0"), cat3, u3a, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("upconv3.conv.3"), u3a, u3b, 0, st));
+  B2O_RETURN_IF(upsample_run(ctx, u3b, cat4_y, st));
+  B2O_RETURN_IF(conv_run(ctx, L("upconv4.conv.0"), cat4, u4a, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("upconv4.conv.3"), u4a, u4b, 0, st));
+  // head (392-410)
+  B2O_RETURN_IF(conv_run(ctx, L("conv_cls.0"), u4b, h1, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_cls.2"), h1, h2, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_cls.4"), h2, h3, 0, st));
+  B2O_RETURN_IF(head_tail_run(ctx, L("conv_cls.6"), L("conv_cls.8"), h3, scores, st));
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+extern "C" size_t b2o_crnn_workspace_bytes(int b) { return b > 0 ? plan_crnn(b).bytes : 0; }
+
+extern "C" int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in, int b, int32_t* labels, void* ws, size_t ws_bytes,
+                                void* stream) {
+  if (!ctx) return B2O_ERR_ARG;
+  if (!ctx->crnn_loaded) { ctx->set_error("b2o_crnn_forward: CRNN weights not loaded"); return B2O_ERR_STATE; }
+  if (b == 0) return B2O_OK;
+  if (!crnn_in || !labels || !ws || b < 0) { ctx->set_error("b2o_crnn_forward: bad argument"); return B2O_ERR_ARG; }
+  const CrnnPlan p = plan_crnn(b);
+  if (ws_bytes < p.bytes) { ctx->set_error("b2o_crnn_forward: workspace too small"); return B2O_ERR_WORKSPACE; }
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+  auto V = [&](size_t off, int nn, int hh, int ww, int c) { return make_view(base + off, nn, hh, ww, c); };
+  auto L = [&](const char* name) -> const ConvLayer& { return ctx->crnn[name]; };
+  const TensorView x1 = V(p.off_x1, b, 200, 31, 64), x2 = V(p.off_x2, b, 200, 31, 128), x3 = V(p.off_x3, b, 200, 31, 256);
+  const TensorView p3 = V(p.off_p3, b, 100, 15, 256), x4 = V(p.off_x4, b, 100, 15, 256), x5 = V(p.off_x5, b, 100, 15, 512);
+  const TensorView p5 = V(p.off_p5, b, 50, 7, 512), x6 = V(p.off_x6, b, 50, 7, 512), x7 = V(p.off_x7, b, 50, 7, 512);
+  const TensorView sa = V(p.off_sa, b, 50, 7, 16), sb = V(p.off_sb, b, 50, 7, 32);
+  // conv stack (recognition.py:217-242)
+  B2O_RETURN_IF(stem_crnn_run(ctx, L("conv_1"), reinterpret_cast<const __half*>(crnn_in), b, x1, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_2"), x1, x2, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_3"), x2, x3, 0, st));
+  B2O_RETURN_IF(maxpool2_run(ctx, x3, p3, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_4"), p3, x4, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_5"), x4, x5, 0, st));
+  B2O_RETURN_IF(maxpool2_run(ctx, x5, p5, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_6"), p5, x6, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_7"), x6, x7, 0, st));
+  // spatial transformer (263-281)
+  B2O_RETURN_IF(conv_run(ctx, L("stn.conv_a"), x7, sa, 0, st));
+  B2O_RETURN_IF(conv_simt_run(ctx, L("stn.conv_b"), sa, sb, 0, st));
+  const TensorView sb_flat = make_view(base + p.off_sb, 1, 1, b, 11200), d1 = make_view(base + p.off_d1, 1, 1, b, 64);
+  B2O_RETURN_IF(conv_run(ctx, L("stn.dense_a"), sb_flat, d1, 0, st));
+  float* theta = reinterpret_cast<float*>(base + p.off_theta);
+  B2O_RETURN_IF(stn_theta_run(ctx, d1.ptr, b, theta, st));
+  __half* warped = reinterpret_cast<__half*>(base + p.off_warp);
+  B2O_RETURN_IF(stn_sample_run(ctx, x7.ptr, theta, b, warped, st));
+  // reshape + fc_9 (282-290)
+  const TensorView seq_in = make_view(warped, 1, 1, b * 50, 3584), fc9 = make_view(base + p.off_fc9, 1, 1, b * 50, 128);
+  B2O_RETURN_IF(conv_run(ctx, L("fc_9"), seq_in, fc9, 0, st));
+  // BiLSTM (292-319)
+  const TensorView xw1 = make_view(base + p.off_xw1, 1, 1, b * 50, 1024);
+  TensorView xw1v = xw1;      // fp32 output: the view's pointer arithmetic is done by the engine in floats
+  B2O_RETURN_IF(conv_run(ctx, L("lstm_in_1"), fc9, xw1v, 1, st));
+  __half* hf = reinterpret_cast<__half*>(base + p.off_hf);
+  __half* hb = reinterpret_cast<__half*>(base + p.off_hb);
+  __half* l1 = reinterpret_cast<__half*>(base + p.off_l1);
+  const float* xw1f = reinterpret_cast<const float*>(base + p.off_xw1);
+  B2O_RETURN_IF(lstm_run(ctx, xw1f, 1024, 0, ctx->lstm_u[0], b, 0, hf, 128, 0, st));
+  B2O_RETURN_IF(lstm_run(ctx, xw1f, 1024, 512, ctx->lstm_u[1], b, 1, hb, 128, 0, st));
+  B2O_RETURN_IF(add_run(ctx, hf, hb, l1, static_cast<long long>(b) * 50 * 128, st));
+  const TensorView l1v = make_view(l1, 1, 1, b * 50, 128), xw2 = make_view(base + p.off_xw2, 1, 1, b * 50, 1024);
+  B2O_RETURN_IF(conv_run(ctx, L("lstm_in_2"), l1v, xw2, 1, st));
+  const float* xw2f = reinterpret_cast<const float*>(base + p.off_xw2);
+  __half* l2 = reinterpret_cast<__half*>(base + p.off_l2);
+  B2O_RETURN_IF(lstm_run(ctx, xw2f, 1024, 0, ctx->lstm_u[2], b, 0, l2, 256, 0, st));
+  B2O_RETURN_IF(lstm_run(ctx, xw2f, 1024, 512, ctx->lstm_u[3], b, 1, l2, 256, 128, st));
+  // fc_12 + discard + greedy CTC (321-333)
+  B2O_RETURN_IF(fc_ctc_run(ctx, l2, b, reinterpret_cast<float*>(base + p.off_logits), labels, st));
+  return B2O_OK;
+}
+
+extern "C" int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws, int b, void* out, size_t out_bytes, void* stream) {
+  if (!ctx || !name || !ws || !out || b <= 0) return B2O_ERR_ARG;
+  const CrnnPlan p = plan_crnn(b);
+  const size_t B = static_cast<size_t>(b);
+  size_t off = 0, bytes = 0;
+  const std::string s(name);
+  if (s == "features") { off = p.off_x7; bytes = B * 50 * 7 * 512 * 2; }
+  else if (s == "theta") { off = p.off_theta; bytes = B * 6 * 4; }
+  else if (s == "warped") { off = p.off_warp; bytes = B * 50 * 7 * 512 * 2; }
+  else if (s == "fc_9") { off = p.off_fc9; bytes = B * 50 * 128 * 2; }
+  else if (s == "l1") { off = p.off_l1; bytes = B * 50 * 128 * 2; }
+  else if (s == "l2") { off = p.off_l2; bytes = B * 50 * 256 * 2; }
+  else if (s == "logits") { off = p.off_logits; bytes = B * 48 * 37 * 4; }
+  else { ctx->set_error("b2o_crnn_tap: unknown tap " + s); return B2O_ERR_ARG; }
+  if (out_bytes < bytes) { ctx->set_error("b2o_crnn_tap: output too small"); return B2O_ERR_ARG; }
+  B2O_CUDA_CHECK(ctx, cudaMemcpyAsync(out, reinterpret_cast<const uint8_t*>(ws) + off, bytes, cudaMemcpyDeviceToDevice,
+                                      reinterpret_cast<cudaStream_t>(stream)));
+  return B2O_OK;
+}
+
+extern "C" int b2o_conv2d_test(b2o_ctx* ctx, const void* x, int n, int h, int w, int cin, const float* wgt, int cout,
+                               int ksize, int dilation, const float* s1, const float* t1, int relu, const float* s2,
+                               const float* t2, void* out, int engine, void* stream) {
+  if (!ctx || !x || !wgt || !s1 || !t1 || !out) return B2O_ERR_ARG;
+  cudaSetDevice(ctx->device);
+  const size_t owned_before = ctx->owned.size();
+  ConvLayer L;
+  auto wget = [wgt, cin, ksize](int o, int c, int ky, int kx) {
+    return wgt[((static_cast<size_t>(o) * ksize + ky) * ksize + kx) * cin + c];
+  };
+  std::vector<float> vs1(s1, s1 + cout), vt1(t1, t1 + cout), vs2, vt2;
+  if (s2 && t2) { vs2.assign(s2, s2 + cout); vt2.assign(t2, t2 + cout); }
+  int rc = build_layer(ctx, L, "test", cin, cout, ksize, dilation, relu, wget, vs1, vt1, s2 ? &vs2 : nullptr,
+                       s2 ? &vt2 : nullptr, false);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (rc == B2O_OK) {
+    const TensorView in = make_view(const_cast<void*>(x), n, h, w, cin), o = make_view(out, n, h, w, cout);
+    if (engine == B2O_CONV_SIMT) rc = conv_simt_run(ctx, L, in, o, 0, st);
+    else rc = conv_tc_run(ctx, L, in, o, 0, st);
+  }
+  cudaError_t e = cudaStreamSynchronize(st);
+  if (rc == B2O_OK && e != cudaSuccess) { ctx->set_error(std::string("conv2d_test: ") + cudaGetErrorString(e)); rc = B2O_ERR_CUDA; }
+  while (ctx->owned.size() > owned_before) { cudaFree(ctx->owned.back()); ctx->owned.pop_back(); }
+  return rc;
+}

@@ -1,0 +1,102 @@
+// Shared declarations for the b2ocr CUDA library (sm_100a only).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/b2ocr.h"
+
+#define B2O_CUDA_CHECK(ctx, expr)                                                              \
+  do {                                                                                         \
+    cudaError_t _e = (expr);                                                                   \
+    if (_e != cudaSuccess) {                                                                   \
+      (ctx)->set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                    \
+      return B2O_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define B2O_LAUNCH_CHECK(ctx)                                                                  \
+  do {                                                                                         \
+    (ctx)->launches++;                                                                         \
+    cudaError_t _e = cudaGetLastError();                                                       \
+    if (_e != cudaSuccess) {                                                                   \
+      (ctx)->set_error(std::string(__FILE__) + ":" + std::to_string(__LINE__) + " launch: " +  \
+                       cudaGetErrorString(_e));                                                \
+      return B2O_ERR_CUDA;                                                                     \
+    }                                                                                          \
+  } while (0)
+
+#define B2O_RETURN_IF(expr)                                                                    \
+  do {                                                                                         \
+    int _s = (expr);                                                                           \
+    if (_s != B2O_OK) return _s;                                                               \
+  } while (0)
+
+// Epilogue applied by every convolution / dense kernel, per output channel n:
+//   y = acc * s1[n] + t1[n];  if (relu) y = max(y, 0);  if (s2) y = y * s2[n] + t2[n]
+// CRAFT conv+BN(+ReLU): s1 = gamma/sqrt(var+eps), t1 = (bias-mean)*s1+beta   (detection.py:87-103)
+// CRNN  conv+ReLU+BN  : s1 = 1, t1 = bias, relu, s2 = gamma/sqrt(var+eps), t2 = beta-mean*s2
+//                       (recognition.py:223-242 -- BN comes AFTER the ReLU there)
+struct ConvLayer {
+  std::string name;
+  int cin = 0, cout = 0, ksize = 1, dil = 1, relu = 0;
+  __half* w_kmajor = nullptr;  // [cout][taps*cin] fp16, K index = tap*cin + c   (tcgen05 B operand)
+  float* w_simt = nullptr;     // [taps][cin][cout] fp32 holding the fp16-rounded values (SIMT engine)
+  float* w_f32 = nullptr;      // [taps][cin][cout] fp32 (only for the 3-channel / 1-channel stems)
+  float *s1 = nullptr, *t1 = nullptr, *s2 = nullptr, *t2 = nullptr;
+  CUtensorMap wmap;            // TMA map over w_kmajor (box 64 x block_n)
+  int block_n = 0;             // tcgen05 N tile; 0 = layer not eligible for the tensor-core engine
+};
+
+struct TensorView {            // NHWC fp16 activation living inside a (possibly wider) buffer
+  __half* ptr = nullptr;       // address of channel 0 of the slice
+  int n = 0, h = 0, w = 0, c = 0;
+  int ld = 0;                  // channel stride of the underlying buffer (elements)
+};
+
+struct b2o_ctx {
+  int device = 0;
+  int sm_count = 148;
+  int conv_engine = B2O_CONV_AUTO;
+  int64_t launches = 0;
+  std::string error;
+  std::map<std::string, ConvLayer> craft, crnn;
+  bool craft_loaded = false, crnn_loaded = false;
+  // CRNN tail parameters (device)
+  float *stn_d2_w = nullptr, *stn_d2_b = nullptr;              // dense 64 -> 6, fp32
+  __half* lstm_u[4] = {nullptr, nullptr, nullptr, nullptr};    // recurrent kernels [128][512] fp16
+  float *fc12_w = nullptr, *fc12_b = nullptr;                  // [256][37], [37] fp32
+  std::vector<void*> owned;    // device allocations freed in b2o_destroy
+  void set_error(const std::string& e) { error = e; }
+};
+
+// ---- engines (conv_tc.cu, conv_simt.cu) -------------------------------------------------------
+int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L);   // builds wmap / picks block_n (0 if ineligible)
+int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
+                int out_f32, cudaStream_t st);
+int conv_simt_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
+                  int out_f32, cudaStream_t st);
+int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
+             int out_f32, cudaStream_t st);
+int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, int h, int w,
+                 const TensorView& out, cudaStream_t st);
+int stem_crnn_run(b2o_ctx* ctx, const ConvLayer& L, const __half* x, int b, const TensorView& out,
+                  cudaStream_t st);
+int maxpool2_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cudaStream_t st);
+int maxpool3s1_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cudaStream_t st);
+int upsample_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cudaStream_t st);
+int head_tail_run(b2o_ctx* ctx, const ConvLayer& L6, const ConvLayer& L8, const TensorView& in,
+                  float* scores, cudaStream_t st);
+
+static inline TensorView make_view(void* base, int n, int h, int w, int c, int ld = 0, int coff = 0) {
+  TensorView v;
+  v.ptr = reinterpret_cast<__half*>(base) + coff;
+  v.n = n; v.h = h; v.w = w; v.c = c; v.ld = ld ? ld : c;
+  return v;
+}

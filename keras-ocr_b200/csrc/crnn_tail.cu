@@ -1,0 +1,231 @@
+// crnn_tail.cu -- the non-convolutional part of the CRNN (reference keras_ocr/recognition.py):
+//   stn_theta_kernel   Dense(64->6) of the localisation net (277)
+//   stn_sample_kernel  _transform (73-166): the reference's bilinear sampler *including its quirks*
+//                      (coordinates scaled by W/H instead of W-1/H-1, weights from clipped corners)
+//   lstm_kernel        keras.layers.LSTM x4 (292-318): gates [i,f,c,o], sigmoid/tanh, go_backwards
+//                      outputs kept in processing order; recurrent matrix column-resident in registers
+//   add_kernel         keras.layers.Add (305)
+//   fc_ctc_kernel      Dense(256->37) (322-327; softmax skipped: argmax-invariant), [:, 2:] (328),
+//                      greedy CTC with repeat merge + blank removal, -1 padding (169-184)
+#include <math.h>
+
+#include "common.cuh"
+
+namespace {
+
+__global__ void stn_theta_kernel(const __half* __restrict__ d1 /*[B][64]*/, int B, const float* __restrict__ w /*[64][6]*/,
+                                 const float* __restrict__ bias, float* __restrict__ theta) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 6) return;
+  const int b = i / 6, k = i - b * 6;
+  float acc = bias[k];
+  for (int c = 0; c < 64; ++c) acc = fmaf(__half2float(d1[b * 64 + c]), w[c * 6 + k], acc);
+  theta[i] = acc;
+}
+
+__device__ __forceinline__ float linspace_pm1(int i, int n) {
+  // torch.linspace(-1, 1, n) in fp32 (symmetric evaluation)
+  const float step = 2.0f / static_cast<float>(n - 1);
+  return (i < n / 2) ? (-1.0f + step * static_cast<float>(i)) : (1.0f - step * static_cast<float>(n - 1 - i));
+}
+
+// feat/out: (B, Hh, Ww, C) fp16 with Hh = 50 ("height" of the STN, the time axis), Ww = 7.
+__global__ void stn_sample_kernel(const __half* __restrict__ feat, const float* __restrict__ theta, int B, int Hh,
+                                  int Ww, int C, __half* __restrict__ out) {
+  const int CV = C / 8;
+  const long long total = static_cast<long long>(B) * Hh * Ww * CV;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % CV);
+  const long long pp = idx / CV;
+  const int ix = static_cast<int>(pp % Ww);
+  const int iy = static_cast<int>((pp / Ww) % Hh);
+  const int b = static_cast<int>(pp / (static_cast<long long>(Ww) * Hh));
+  const float* th = theta + b * 6;
+  const float gx = linspace_pm1(ix, Ww), gy = linspace_pm1(iy, Hh);
+  const float xs = __fadd_rn(__fadd_rn(__fmul_rn(th[0], gx), __fmul_rn(th[1], gy)), th[2]);
+  const float ys = __fadd_rn(__fadd_rn(__fmul_rn(th[3], gx), __fmul_rn(th[4], gy)), th[5]);
+  const float x = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(xs, 1.0f)), static_cast<float>(Ww));
+  const float y = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(ys, 1.0f)), static_cast<float>(Hh));
+  // floor -> int32 cast like tf.cast(tf.floor(x), "int32"); clamp the float first so the cast is defined
+  int x0 = static_cast<int>(floorf(fminf(fmaxf(x, -1.0e6f), 1.0e6f)));
+  int y0 = static_cast<int>(floorf(fminf(fmaxf(y, -1.0e6f), 1.0e6f)));
+  int x1 = x0 + 1, y1 = y0 + 1;
+  x0 = min(max(x0, 0), Ww - 1); x1 = min(max(x1, 0), Ww - 1);
+  y0 = min(max(y0, 0), Hh - 1); y1 = min(max(y1, 0), Hh - 1);
+  const float fx0 = static_cast<float>(x0), fx1 = static_cast<float>(x1);
+  const float fy0 = static_cast<float>(y0), fy1 = static_cast<float>(y1);
+  const float wa = __fmul_rn(fx1 - x, fy1 - y), wb = __fmul_rn(fx1 - x, y - fy0);
+  const float wc = __fmul_rn(x - fx0, fy1 - y), wd = __fmul_rn(x - fx0, y - fy0);
+  const __half* base = feat + static_cast<size_t>(b) * Hh * Ww * C + cv * 8;
+  const uint4 ra = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * Ww + x0) * C);
+  const uint4 rb = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * Ww + x0) * C);
+  const uint4 rc = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * Ww + x1) * C);
+  const uint4 rd = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * Ww + x1) * C);
+  const __half2* pa = reinterpret_cast<const __half2*>(&ra);
+  const __half2* pb = reinterpret_cast<const __half2*>(&rb);
+  const __half2* pc = reinterpret_cast<const __half2*>(&rc);
+  const __half2* pd = reinterpret_cast<const __half2*>(&rd);
+  uint4 r;
+  __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(pa[i]), bb = __half22float2(pb[i]);
+    const float2 c = __half22float2(pc[i]), d = __half22float2(pd[i]);
+    pr[i] = __floats2half2_rn(wa * a.x + wb * bb.x + wc * c.x + wd * d.x, wa * a.y + wb * bb.y + wc * c.y + wd * d.y);
+  }
+  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pp) * C + cv * 8) = r;
+}
+
+// ---------------------------------------------------------------------------------------- LSTM
+constexpr int kUnits = 128, kGates = 512, kSteps = 50;
+constexpr int kCropsPerCta = 8;
+
+__device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+// xw  : (B*T, xw_ld) fp32 input projections x@W + b; this direction's 512 gate columns start at xw_off
+// u   : (128, 512) fp16 recurrent kernel (row k = previous-h unit, column g = gate)
+// out : (B, T, out_ld) fp16, written at channel offset out_off, indexed by PROCESSING step
+__global__ void __launch_bounds__(kGates, 1)
+lstm_kernel(const float* __restrict__ xw, int xw_ld, int xw_off, const __half* __restrict__ u, int B, int backwards,
+            __half* __restrict__ out, int out_ld, int out_off) {
+  __shared__ __align__(16) float h_s[kCropsPerCta][kUnits];
+  __shared__ float z_s[kCropsPerCta][kGates];
+  const int g = threadIdx.x;
+  const int b0 = blockIdx.x * kCropsPerCta;
+  const int nb = min(kCropsPerCta, B - b0);
+  // this thread's column of U, as (k, k+1) pairs
+  __half2 ucol[kUnits / 2];
+#pragma unroll
+  for (int k = 0; k < kUnits / 2; ++k)
+    ucol[k] = __halves2half2(u[(2 * k) * kGates + g], u[(2 * k + 1) * kGates + g]);
+  for (int i = threadIdx.x; i < kCropsPerCta * kUnits; i += blockDim.x) (&h_s[0][0])[i] = 0.0f;
+  float c_state[2] = {0.0f, 0.0f};        // cell state of work items (g) and (g + 512) in the gate phase
+  __syncthreads();
+  for (int step = 0; step < kSteps; ++step) {
+    const int t = backwards ? (kSteps - 1 - step) : step;
+    float acc[kCropsPerCta];
+#pragma unroll
+    for (int b = 0; b < kCropsPerCta; ++b)
+      acc[b] = (b < nb) ? xw[(static_cast<size_t>(b0 + b) * kSteps + t) * xw_ld + xw_off + g] : 0.0f;
+#pragma unroll
+    for (int k = 0; k < kUnits / 2; ++k) {
+      const float2 uk = __half22float2(ucol[k]);
+#pragma unroll
+      for (int b = 0; b < kCropsPerCta; ++b) {
+        const float2 hv = *reinterpret_cast<const float2*>(&h_s[b][2 * k]);
+        acc[b] = fmaf(hv.x, uk.x, acc[b]);
+        acc[b] = fmaf(hv.y, uk.y, acc[b]);
+      }
+    }
+#pragma unroll
+    for (int b = 0; b < kCropsPerCta; ++b) z_s[b][g] = acc[b];
+    __syncthreads();
+    // gate phase: 8 crops x 128 units = 1024 items over 512 threads
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      const int item = g + r * kGates;
+      const int b = item / kUnits, j = item - b * kUnits;
+      if (b < nb) {
+        const float zi = z_s[b][j], zf = z_s[b][kUnits + j], zc = z_s[b][2 * kUnits + j], zo = z_s[b][3 * kUnits + j];
+        const float c = sigmoidf_acc(zf) * c_state[r] + sigmoidf_acc(zi) * tanhf(zc);
+        const float h = sigmoidf_acc(zo) * tanhf(c);
+        c_state[r] = c;
+        h_s[b][j] = h;
+        out[(static_cast<size_t>(b0 + b) * kSteps + step) * out_ld + out_off + j] = __float2half_rn(h);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+__global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restrict__ b, __half2* __restrict__ o, long long n2) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n2) return;
+  const float2 x = __half22float2(a[i]), y = __half22float2(b[i]);
+  o[i] = __floats2half2_rn(x.x + y.x, x.y + y.y);
+}
+
+// ---------------------------------------------------------------------------------------- fc_12 + CTC
+constexpr int kClasses = 37, kKeep = 48, kDiscard = 2, kFeat = 256;
+
+__global__ void __launch_bounds__(64)
+fc_ctc_kernel(const __half* __restrict__ l2 /*[B][50][256]*/, const float* __restrict__ w /*[256][37]*/,
+              const float* __restrict__ bias, int B, float* __restrict__ logits /*[B][48][37] or null*/,
+              int* __restrict__ labels /*[B][48]*/) {
+  __shared__ int best[kKeep];
+  const int b = blockIdx.x;
+  const int t = threadIdx.x;                       // one thread per kept time step
+  if (t < kKeep) {
+    const __half* x = l2 + (static_cast<size_t>(b) * kSteps + t + kDiscard) * kFeat;
+    float acc[kClasses];
+#pragma unroll
+    for (int k = 0; k < kClasses; ++k) acc[k] = bias[k];
+    for (int c = 0; c < kFeat; ++c) {
+      const float xv = __half2float(x[c]);
+      const float* wr = w + c * kClasses;
+#pragma unroll
+      for (int k = 0; k < kClasses; ++k) acc[k] = fmaf(xv, __ldg(wr + k), acc[k]);
+    }
+    int arg = 0;
+    float mx = acc[0];
+#pragma unroll
+    for (int k = 1; k < kClasses; ++k)
+      if (acc[k] > mx) { mx = acc[k]; arg = k; }   // first maximum wins
+    best[t] = arg;
+    if (logits) {
+      float* lo = logits + (static_cast<size_t>(b) * kKeep + t) * kClasses;
+#pragma unroll
+      for (int k = 0; k < kClasses; ++k) lo[k] = acc[k];
+    }
+  }
+  __syncthreads();
+  if (t == 0) {
+    int* o = labels + static_cast<size_t>(b) * kKeep;
+    int n = 0, prev = -1;
+    for (int s = 0; s < kKeep; ++s) {
+      const int c = best[s];
+      if (c != kClasses - 1 && c != prev) o[n++] = c;
+      prev = c;
+    }
+    for (; n < kKeep; ++n) o[n] = -1;
+  }
+}
+
+inline unsigned nb(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
+
+}  // namespace
+
+int stn_theta_run(b2o_ctx* ctx, const __half* d1, int B, float* theta, cudaStream_t st) {
+  stn_theta_kernel<<<nb(B * 6, 128), 128, 0, st>>>(d1, B, ctx->stn_d2_w, ctx->stn_d2_b, theta);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+int stn_sample_run(b2o_ctx* ctx, const __half* feat, const float* theta, int B, __half* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(B) * 50 * 7 * (512 / 8);
+  stn_sample_kernel<<<nb(total, 256), 256, 0, st>>>(feat, theta, B, 50, 7, 512, out);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+int lstm_run(b2o_ctx* ctx, const float* xw, int xw_ld, int xw_off, const __half* u, int B, int backwards, __half* out,
+             int out_ld, int out_off, cudaStream_t st) {
+  lstm_kernel<<<(B + kCropsPerCta - 1) / kCropsPerCta, kGates, 0, st>>>(xw, xw_ld, xw_off, u, B, backwards, out, out_ld,
+                                                                        out_off);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+int add_run(b2o_ctx* ctx, const __half* a, const __half* b, __half* o, long long n, cudaStream_t st) {
+  add_kernel<<<nb(n / 2, 256), 256, 0, st>>>(reinterpret_cast<const __half2*>(a), reinterpret_cast<const __half2*>(b),
+                                             reinterpret_cast<__half2*>(o), n / 2);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+int fc_ctc_run(b2o_ctx* ctx, const __half* l2, int B, float* logits, int* labels, cudaStream_t st) {
+  fc_ctc_kernel<<<B, 64, 0, st>>>(l2, ctx->fc12_w, ctx->fc12_b, B, logits, labels);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}

@@ -1,0 +1,122 @@
+"""Pipeline: drop-in for ``keras_ocr.pipeline.Pipeline`` (reference pipeline.py:7-75)."""
+import numpy as np
+import torch
+
+from . import detection, recognition, tools
+
+
+class Pipeline:
+    """A wrapper for a combination of detector and recognizer.
+
+    Args:
+        detector: The detector to use (default: ``detection.Detector()``)
+        recognizer: The recognizer to use (default: ``recognition.Recognizer()``)
+        scale: The scale factor to apply to input images
+        max_size: The maximum single-side dimension of images for inference.
+
+    Any object with ``detect`` / ``recognize_from_boxes`` can be injected, as in the reference
+    (pipeline.py:18-26, 62-65); with this package's own Detector and Recognizer the whole call
+    stays on the GPU between the host->device copy of the images and the device->host copy of
+    (counts, boxes, labels).
+    """
+
+    def __init__(self, detector=None, recognizer=None, scale=2, max_size=2048):
+        if detector is None:
+            detector = detection.Detector()
+        if recognizer is None:
+            recognizer = recognition.Recognizer()
+        self.scale = scale
+        self.detector = detector
+        self.recognizer = recognizer
+        self.max_size = max_size
+        self.last_stats = {}
+
+    def _native(self):
+        return isinstance(self.detector, detection.Detector) and isinstance(self.recognizer, recognition.Recognizer)
+
+    def prepare_device(self, images):
+        """resize_image + pad (pipeline.py:44-57) on the GPU.  Returns ((N,H,W,3) u8 CUDA tensor, scales)."""
+        det = self.detector
+        plans = [tools.resize_plan(image.shape, self.scale, self.max_size) for image in images]
+        scales = [p[0] for p in plans]
+        hp, wp = max(p[1] for p in plans), max(p[2] for p in plans)
+        n = len(images)
+        stream = torch.cuda.current_stream(det.device).cuda_stream
+        batch = torch.empty((n, hp, wp, 3), dtype=torch.uint8, device=det.device)
+        same = isinstance(images, np.ndarray) and images.ndim == 4
+        h2d = 0
+        if same:
+            src_all = torch.from_numpy(np.ascontiguousarray(images)).pin_memory().to(det.device, non_blocking=True)
+            h2d = src_all.numel()
+        for i, image in enumerate(images):
+            if same:
+                src = src_all[i]
+            else:
+                assert image.ndim == 3 and image.shape[2] == 3 and image.dtype == np.uint8, "images must be HxWx3 uint8"
+                src = torch.from_numpy(np.ascontiguousarray(image)).pin_memory().to(det.device, non_blocking=True)
+                h2d += src.numel()
+            _, hr, wr = plans[i]
+            det.ctx.resize_pad(src.data_ptr(), image.shape[0], image.shape[1], hr, wr, batch.data_ptr(), i, hp, wp, stream)
+        self.last_stats["h2d_bytes"] = int(h2d)
+        return batch, scales
+
+    def recognize(self, images, detection_kwargs=None, recognition_kwargs=None):
+        """Run the pipeline on one or multiple images (reference pipeline.py:28-75).
+
+        Returns a list (one entry per image) of lists of (text, box) tuples, boxes (4,2) float32 in
+        the coordinates of the *input* image.
+        """
+        if not isinstance(images, np.ndarray):
+            images = [tools.read(image) for image in images]
+        if detection_kwargs is None:
+            detection_kwargs = {}
+        if recognition_kwargs is None:
+            recognition_kwargs = {}
+        if not self._native():
+            return self._recognize_generic(images, detection_kwargs, recognition_kwargs)
+        det, rec = self.detector, self.recognizer
+        batch, scales = self.prepare_device(images)
+        thresholds = {k: detection_kwargs[k] for k in ("detection_threshold", "text_threshold", "link_threshold",
+                                                        "size_threshold") if k in detection_kwargs}
+        boxes, counts = det.detect_device(batch, **thresholds)
+        labels = rec.recognize_from_boxes_device(batch, boxes, counts)
+        boxes_host = boxes.cpu().numpy()
+        d2h = boxes_host.nbytes + counts.nbytes
+        if labels is not None:
+            labels_host = labels.cpu().numpy()
+            d2h += labels_host.nbytes
+            texts = recognition.labels_to_text(labels_host, rec.alphabet)
+        else:
+            texts = []
+        self.last_stats["d2h_bytes"] = int(d2h)
+        out, start = [], 0
+        for i, (c, scale) in enumerate(zip(counts, scales)):
+            c = int(c)
+            group = boxes_host[i, :c]
+            if scale != 1:
+                group = tools.adjust_boxes(boxes=group, boxes_format="boxes", scale=1 / scale)
+            out.append(list(zip(texts[start:start + c], group)))
+            start += c
+        return out
+
+    def _recognize_generic(self, images, detection_kwargs, recognition_kwargs):
+        """Reference flow for injected (duck-typed) detectors / recognizers: host arrays between stages."""
+        import cv2
+
+        resized = []
+        for image in images:
+            scale, hr, wr = tools.resize_plan(image.shape, self.scale, self.max_size)
+            resized.append((cv2.resize(image, dsize=(wr, hr)), scale))
+        max_height, max_width = np.array([im.shape[:2] for im, _ in resized]).max(axis=0)
+        scales = [s for _, s in resized]
+        padded = []
+        for im, _ in resized:
+            canvas = np.zeros((max_height, max_width, 3), dtype=im.dtype) + 255
+            canvas[: im.shape[0], : im.shape[1]] = im
+            padded.append(canvas)
+        batch = np.array(padded)
+        box_groups = self.detector.detect(images=batch, **detection_kwargs)
+        prediction_groups = self.recognizer.recognize_from_boxes(images=batch, box_groups=box_groups, **recognition_kwargs)
+        box_groups = [tools.adjust_boxes(boxes=boxes, boxes_format="boxes", scale=1 / scale) if scale != 1 else boxes
+                      for boxes, scale in zip(box_groups, scales)]
+        return [list(zip(predictions, boxes)) for predictions, boxes in zip(prediction_groups, box_groups)]

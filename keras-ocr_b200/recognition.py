@@ -1,0 +1,133 @@
+"""Recognizer: drop-in for ``keras_ocr.recognition.Recognizer`` (reference recognition.py:353-537)."""
+import string
+import typing
+
+import numpy as np
+import torch
+
+from . import _lib, tools, weights as weights_mod
+
+DEFAULT_ALPHABET = string.digits + string.ascii_lowercase      # reference recognition.py:25
+TARGET_HEIGHT, TARGET_WIDTH, STEPS = 31, 200, 48                # DEFAULT_BUILD_PARAMS, recognition.py:13-23
+
+
+def labels_to_text(rows, alphabet=DEFAULT_ALPHABET):
+    """reference recognition.py:527-534."""
+    blank = len(alphabet)
+    return ["".join(alphabet[idx] for idx in row if idx not in (blank, -1)) for row in rows]
+
+
+class Recognizer:
+    """A text recognizer using the CRNN architecture, running as sm_100a CUDA kernels.
+
+    Args:
+        alphabet: only the default ``0-9a-z`` alphabet is built (the kernels fix 37 classes).
+        weights: ``"kurapan"`` needs a converted ``crnn_kurapan.npz`` in the cache dir (Keras ``.h5``
+            cannot be read without h5py); otherwise a ``.npz`` path or a dict keyed like ``weights.py``.
+        build_params: must be ``None`` / the defaults (reference recognition.py:13-23).
+    """
+
+    def __init__(self, alphabet=None, weights="kurapan", build_params=None, device=None):
+        assert alphabet or weights, "At least one of alphabet or weights must be provided."
+        if alphabet is not None and alphabet != DEFAULT_ALPHABET:
+            raise NotImplementedError("only the default alphabet is supported by the CUDA recognizer")
+        if build_params is not None:
+            raise NotImplementedError("only DEFAULT_BUILD_PARAMS are supported by the CUDA recognizer")
+        if not torch.cuda.is_available():
+            raise _lib.B2OError("keras-ocr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.alphabet = DEFAULT_ALPHABET
+        self.blank_label_idx = len(self.alphabet)
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        if isinstance(weights, dict):
+            tensors = weights
+        elif isinstance(weights, str) and weights.endswith(".npz"):
+            tensors = weights_mod.load_npz(weights)
+        elif weights == "kurapan":
+            tensors = weights_mod.load_npz(tools.find_cached("crnn_kurapan.npz"))
+        else:
+            raise NotImplementedError(f"Cannot load weights from {weights}")
+        self.ctx = _lib.Context(self.device_index)
+        self.ctx.load_crnn(tensors)
+        self.keep_workspace = False      # tests set this to read intermediate taps
+        self._last_ws = None
+
+    # ------------------------------------------------------------------ device-resident API
+    def gray_device(self, images_t):
+        n, h, w, _ = images_t.shape
+        gray = torch.empty((n, h, w), dtype=torch.uint8, device=self.device)
+        self.ctx.rgb_to_gray(images_t.data_ptr(), n, h, w, gray.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        return gray
+
+    def warp_device(self, gray, boxes_flat, image_index, want_crops=False):
+        """tools.warpBox for every box.  Returns (crnn_in (B,200,31) fp16, crops (B,31,200) u8 or None)."""
+        n, h, w = gray.shape
+        b = boxes_flat.shape[0]
+        crnn_in = torch.empty((b, TARGET_WIDTH, TARGET_HEIGHT), dtype=torch.float16, device=self.device)
+        crops = torch.empty((b, TARGET_HEIGHT, TARGET_WIDTH), dtype=torch.uint8, device=self.device) if want_crops else None
+        self.ctx.warp_boxes(gray.data_ptr(), n, h, w, boxes_flat.data_ptr(), image_index.data_ptr(), b,
+                            crops.data_ptr() if want_crops else None, crnn_in.data_ptr(),
+                            torch.cuda.current_stream(self.device).cuda_stream)
+        return crnn_in, crops
+
+    def predict_device(self, crnn_in):
+        """CRNN + greedy CTC.  crnn_in: (B,200,31) fp16 -> labels (B,48) int32 (-1 padded)."""
+        b = crnn_in.shape[0]
+        labels = torch.empty((b, STEPS), dtype=torch.int32, device=self.device)
+        nbytes = self.ctx.crnn_workspace_bytes(b)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self.ctx.crnn_forward(crnn_in.data_ptr(), b, labels.data_ptr(), ws.data_ptr(), nbytes,
+                              torch.cuda.current_stream(self.device).cuda_stream)
+        self._last_ws = (ws, b) if self.keep_workspace else None
+        return labels
+
+    def tap(self, name, shape, dtype):
+        """Debug: copy an intermediate of the last predict_device call (needs keep_workspace=True)."""
+        ws, b = self._last_ws
+        out = torch.empty(shape, dtype=dtype, device=self.device)
+        self.ctx.crnn_tap(name, ws.data_ptr(), b, out.data_ptr(), out.numel() * out.element_size(),
+                          torch.cuda.current_stream(self.device).cuda_stream)
+        return out
+
+    def recognize_crops(self, crops):
+        """crops: (B,31,200) uint8 (ndarray or tensor), i.e. what tools.warpBox returns -> list[str]."""
+        t = crops if isinstance(crops, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(crops))
+        t = t.to(self.device).contiguous()
+        b = t.shape[0]
+        if b == 0:
+            return []
+        crnn_in = torch.empty((b, TARGET_WIDTH, TARGET_HEIGHT), dtype=torch.float16, device=self.device)
+        self.ctx.crops_to_input(t.data_ptr(), b, crnn_in.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        return labels_to_text(self.predict_device(crnn_in).cpu().numpy(), self.alphabet)
+
+    def recognize_from_boxes_device(self, images_t, boxes, counts):
+        """images_t (N,H,W,3) u8 CUDA; boxes (N,M,4,2) f32 CUDA; counts host ndarray -> labels (B,48) i32 CUDA."""
+        counts = np.asarray(counts)
+        total = int(counts.sum())
+        if total == 0:
+            return None
+        idx = np.repeat(np.arange(len(counts), dtype=np.int32), counts)
+        image_index = torch.from_numpy(idx).to(self.device, non_blocking=True)
+        m = boxes.shape[1]
+        slot = np.concatenate([np.arange(c, dtype=np.int64) for c in counts]) + idx.astype(np.int64) * m
+        flat = boxes.reshape(-1, 4, 2).index_select(0, torch.from_numpy(slot).to(self.device, non_blocking=True)).contiguous()
+        crnn_in, _ = self.warp_device(self.gray_device(images_t), flat, image_index)
+        return self.predict_device(crnn_in)
+
+    # ------------------------------------------------------------------ reference API
+    def recognize_from_boxes(self, images, box_groups, **kwargs) -> typing.List[typing.List[str]]:
+        """Same contract as reference recognition.py:491-537."""
+        assert len(box_groups) == len(images), "You must provide the same number of box groups as images."
+        from .detection import _as_device_images
+
+        images_t = _as_device_images(images, self.device)
+        counts = np.array([len(b) for b in box_groups], dtype=np.int64)
+        if counts.sum() == 0:
+            return [[]] * len(images)
+        flat = np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 4, 2) for b in box_groups if len(b)])
+        flat_t = torch.from_numpy(np.ascontiguousarray(flat)).to(self.device)
+        idx = torch.from_numpy(np.repeat(np.arange(len(counts), dtype=np.int32), counts)).to(self.device)
+        crnn_in, _ = self.warp_device(self.gray_device(images_t), flat_t, idx)
+        predictions = labels_to_text(self.predict_device(crnn_in).cpu().numpy(), self.alphabet)
+        ends = np.cumsum(counts)
+        return [predictions[int(e - c):int(e)] for c, e in zip(counts, ends)]

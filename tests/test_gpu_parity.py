@@ -1,0 +1,280 @@
+"""GPU parity tests: every CUDA stage, called through the C-ABI, against the CPU oracle and the
+golden vectors generated from the reference.  Run on the B200 box: ``pytest tests -m gpu``.
+
+Tolerances (stated per test): integer/byte/index work is bit-exact; fp16 tensor-core stages are
+compared with the fp32 oracle at the tolerances proposed in SURVEY.md 8(c).
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from keras_ocr_b200 import _lib, weights as W
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.fixture(scope="module")
+def ctx(cuda_device):
+    c = _lib.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def detector(cuda_device):
+    from keras_ocr_b200.detection import Detector
+    return Detector(weights=W.synthetic_craft_weights(seed=3))
+
+
+@pytest.fixture(scope="module")
+def recognizer(cuda_device):
+    from keras_ocr_b200.recognition import Recognizer
+    r = Recognizer(weights=W.synthetic_crnn_weights(seed=2))
+    r.keep_workspace = True
+    return r
+
+
+# ------------------------------------------------------------------------------- conv engines
+CONV_CASES = [
+    # n, h, w, cin, cout, k, dil, relu, affine2
+    (2, 16, 16, 64, 64, 3, 1, 1, 0),
+    (1, 24, 40, 128, 256, 3, 1, 1, 0),
+    (1, 9, 13, 512, 1024, 3, 6, 0, 0),      # dilated slice5.1 shape, odd spatial size
+    (3, 17, 23, 64, 32, 3, 1, 1, 0),        # ragged tiles, batch-spanning boxes
+    (2, 50, 7, 512, 16, 5, 1, 1, 0),        # STN conv_a: 5x5, tiny cout, W smaller than the box
+    (2, 50, 7, 512, 512, 3, 1, 1, 1),       # CRNN conv_7: ReLU then BN affine
+    (1, 1, 300, 3584, 128, 1, 1, 1, 0),     # fc_9 as a 1x1 conv over rows
+    (1, 8, 8, 1536, 512, 1, 1, 1, 0),       # upconv1.conv.0
+    (1, 96, 96, 64, 64, 3, 1, 1, 0),        # many tiles per CTA (persistent loop, both TMEM stages)
+]
+
+
+def _torch_conv_reference(x, wgt, k, dil, s1, t1, relu, s2, t2):
+    xt = x.float().permute(0, 3, 1, 2)
+    wt = torch.from_numpy(wgt).to(x.device).half().float().permute(0, 3, 1, 2)      # (cout,cin,k,k), fp16-rounded
+    y = torch.nn.functional.conv2d(xt, wt, padding=dil * (k // 2), dilation=dil)
+    y = y * torch.from_numpy(s1).to(x.device)[None, :, None, None] + torch.from_numpy(t1).to(x.device)[None, :, None, None]
+    if relu:
+        y = torch.relu(y)
+    if s2 is not None:
+        y = y * torch.from_numpy(s2).to(x.device)[None, :, None, None] + torch.from_numpy(t2).to(x.device)[None, :, None, None]
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+@pytest.mark.parametrize("engine", [_lib.CONV_SIMT, _lib.CONV_AUTO], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[f"n{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}_k{c[5]}d{c[6]}" for c in CONV_CASES])
+def test_conv_engine_vs_fp32(ctx, cuda_device, case, engine):
+    n, h, w, cin, cout, k, dil, relu, aff = case
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    rng = np.random.default_rng(hash(case) % (2 ** 31))
+    x = torch.from_numpy(rng.standard_normal((n, h, w, cin)).astype(np.float32)).to(cuda_device).half().contiguous()
+    wgt = (rng.standard_normal((cout, k, k, cin)) * np.sqrt(2.0 / (cin * k * k))).astype(np.float32)
+    s1 = rng.uniform(0.7, 1.3, cout).astype(np.float32)
+    t1 = (rng.standard_normal(cout) * 0.2).astype(np.float32)
+    s2 = rng.uniform(0.7, 1.3, cout).astype(np.float32) if aff else None
+    t2 = (rng.standard_normal(cout) * 0.2).astype(np.float32) if aff else None
+    out = torch.full((n, h, w, cout), float("nan"), dtype=torch.float16, device=cuda_device)
+    ctx.conv2d_test(x.data_ptr(), n, h, w, cin, wgt, cout, k, dil, s1, t1, relu, s2, t2, out.data_ptr(), engine, _stream())
+    torch.cuda.synchronize()
+    ref = _torch_conv_reference(x, wgt, k, dil, s1, t1, relu, s2, t2)
+    err = (out.float() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert np.isfinite(err), "NaN/unwritten output"
+    # fp32 accumulation, one fp16 rounding of the result: |err| <= 2^-10 * |y| (+ accumulation-order noise)
+    assert err <= 2.5e-3 * max(scale, 1.0), (err, scale)
+
+
+# ------------------------------------------------------------------------------- image stages
+@pytest.mark.parametrize("tag", ["x2", "capped", "x3"])
+def test_resize_pad_bit_exact(ctx, cuda_device, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "inputs.npz"))
+    src, ref = g[f"resize_{tag}_src"], g[f"resize_{tag}_dst"]
+    hr, wr = ref.shape[:2]
+    hp, wp = hr + 5, wr + 9
+    src_t = torch.from_numpy(src).to(cuda_device)
+    dst = torch.zeros((2, hp, wp, 3), dtype=torch.uint8, device=cuda_device)
+    ctx.resize_pad(src_t.data_ptr(), src.shape[0], src.shape[1], hr, wr, dst.data_ptr(), 1, hp, wp, _stream())
+    out = dst.cpu().numpy()[1]
+    assert np.array_equal(out[:hr, :wr], ref)                       # cv2.resize, bit-exact
+    assert (out[hr:] == 255).all() and (out[:, wr:] == 255).all()   # tools.pad cval=255
+    with pytest.raises(_lib.B2OError):                              # tools.pad's assert: target smaller than image
+        ctx.resize_pad(src_t.data_ptr(), src.shape[0], src.shape[1], hr, wr, dst.data_ptr(), 0, hr - 1, wr, _stream())
+
+
+def test_gray_bit_exact(ctx, cuda_device):
+    from oracle import imageops
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (2, 37, 53, 3), dtype=np.uint8)
+    t = torch.from_numpy(img).to(cuda_device)
+    gray = torch.empty((2, 37, 53), dtype=torch.uint8, device=cuda_device)
+    ctx.rgb_to_gray(t.data_ptr(), 2, 37, 53, gray.data_ptr(), _stream())
+    assert np.array_equal(gray.cpu().numpy(), np.stack([imageops.rgb_to_gray(i) for i in img]))
+
+
+def test_warp_boxes_vs_reference_golden(recognizer, cuda_device, golden_dir):
+    g = np.load(os.path.join(golden_dir, "warp.npz"))
+    gray = torch.from_numpy(g["warp_gray"][None]).to(cuda_device).contiguous()
+    quads = torch.from_numpy(g["warp_quads"]).to(cuda_device).contiguous()
+    idx = torch.zeros(len(g["warp_quads"]), dtype=torch.int32, device=cuda_device)
+    crnn_in, crops = recognizer.warp_device(gray, quads, idx, want_crops=True)
+    crops = crops.cpu().numpy()
+    ref = g["warp_crops"]
+    diff = np.abs(crops.astype(int) - ref.astype(int))
+    # cv2 solves the homography with a slightly different elimination order (last-ulp differences in
+    # M), so a coordinate can land on the other side of a 1/32-pixel rounding: <= 1 level, <= 0.1 %.
+    assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3, (diff.max(), (diff > 0).mean())
+    # CRNN input layout: x[b, t, j] = crop[b, 30 - j, t] / 255   (recognition.py:215-216, 524)
+    expect = (crops[:, ::-1, :].transpose(0, 2, 1).astype(np.float32) / 255).astype(np.float16)
+    assert np.array_equal(crnn_in.cpu().numpy(), expect)
+
+
+# ------------------------------------------------------------------------------- getBoxes
+def _match_quads(mine, ref):
+    """max corner distance allowing a cyclic shift of the starting corner (argmin(x+y) ties)."""
+    return min(np.abs(np.roll(mine, s, 0) - ref).max() for s in range(4))
+
+
+def _check_boxes(detector, scores, ref_groups, tol=1e-3):
+    t = torch.from_numpy(np.ascontiguousarray(scores)).to(detector.device)
+    boxes, counts = detector.boxes_device(t)
+    boxes = boxes.cpu().numpy()
+    assert list(counts) == [len(r) for r in ref_groups]            # same components kept, same order
+    worst = 0.0
+    for i, ref in enumerate(ref_groups):
+        for k in range(len(ref)):
+            worst = max(worst, _match_quads(boxes[i, k], ref[k]))
+    assert worst <= tol, worst
+
+
+@pytest.mark.parametrize("tag", ["grid32", "rot12", "dense", "blank", "refmaps"])
+def test_get_boxes_vs_reference_golden(detector, golden_dir, tag):
+    g = np.load(os.path.join(golden_dir, "boxes.npz"))
+    counts = g[f"boxes_{tag}_counts"]
+    quads = g[f"boxes_{tag}_quads"]
+    groups, start = [], 0
+    for c in counts:
+        groups.append(quads[start:start + c])
+        start += c
+    _check_boxes(detector, g[f"boxes_{tag}_scores"], groups)
+
+
+def test_get_boxes_vs_oracle_large_and_adversarial(detector):
+    from oracle import imageops, synth
+    maps = synth.score_maps(101, 2, 768, 768, 32)
+    # adversarial: component of area 9 / 10 / 11, max text 0.699 / 0.701, border-touching blob,
+    # a word split in two by text&link removal, a near-square "diamond" blob
+    adv = np.zeros((1, 160, 200, 2), np.float32)
+    adv[0, 10:13, 10:13, 0] = 0.9                       # area 9  -> dropped (size_threshold)
+    adv[0, 10:12, 30:35, 0] = 0.9                       # area 10 -> kept
+    adv[0, 20:25, 60:70, 0] = 0.699                     # max below detection threshold -> dropped
+    adv[0, 20:25, 90:100, 0] = 0.701                    # kept
+    adv[0, 0:8, 150:200, 0] = 0.8                       # touches top and right borders
+    adv[0, 60:70, 20:120, 0] = 0.8                      # long word ...
+    adv[0, 60:70, 60:80, 1] = 0.9                       # ... whose middle is text & link (removed, 246)
+    adv[0, 100:130, 40:70, 0] = 0.85                    # square blob -> "diamond" branch (276-281)
+    yy, xx = np.mgrid[0:160, 0:200]
+    adv[0, ..., 0] = np.maximum(adv[0, ..., 0], 0.9 * (np.abs(yy - 120) + np.abs(xx - 150) < 18))   # rotated square
+    for scores in (maps, adv):
+        _check_boxes(detector, scores, imageops.get_boxes(scores))
+
+
+def test_get_boxes_overflow_retry(detector):
+    from oracle import imageops, synth
+    maps = synth.score_maps(7, 1, 256, 256, 40)
+    detector.max_boxes = 4                               # force the count > max_boxes retry path
+    try:
+        _check_boxes(detector, maps, imageops.get_boxes(maps))
+        assert detector.max_boxes >= 32
+    finally:
+        detector.max_boxes = 256
+
+
+# ------------------------------------------------------------------------------- CRAFT
+@pytest.mark.parametrize("engine", [_lib.CONV_SIMT, _lib.CONV_AUTO], ids=["simt", "tcgen05"])
+def test_craft_forward_vs_reference_golden(detector, golden_dir, engine):
+    g = np.load(os.path.join(golden_dir, "craft.npz"))
+    detector.ctx.set_conv_engine(engine)
+    try:
+        for tag in ("even", "odd"):
+            img = torch.from_numpy(g[f"craft_{tag}_image"]).to(detector.device)
+            scores = detector.predict_device(img).cpu().numpy()
+            ref = g[f"craft_{tag}_scores"]              # output of the reference's own torch CRAFT, fp32
+            assert scores.shape == ref.shape
+            err = np.abs(scores - ref).max() / max(np.abs(ref).max(), 1.0)
+            # fp16 activations through 27 layers vs fp32: <= 2e-2 of the map's range
+            assert err <= 2e-2, (tag, err)
+    finally:
+        detector.ctx.set_conv_engine(_lib.CONV_AUTO)
+
+
+# ------------------------------------------------------------------------------- CRNN
+def test_crnn_vs_oracle(recognizer):
+    from oracle import crnn
+    wts = W.synthetic_crnn_weights(seed=2)
+    rng = np.random.default_rng(5)
+    b = 6
+    crops = rng.integers(0, 256, (b, 31, 200), dtype=np.uint8)
+    crops[:, :, 150:] = 0                                   # zero tail like a real warpBox crop
+    texts = recognizer.recognize_crops(crops)
+    with torch.no_grad():
+        probs, inter = crnn.crnn_logits(wts, crops.astype(np.float32) / 255, return_intermediates=True)
+    dev = recognizer.device
+
+    def rel(a, ref):
+        return float((a - ref).abs().max() / max(ref.abs().max(), 1e-6))
+
+    feat = recognizer.tap("features", (b, 50, 7, 512), torch.float16).float().cpu()
+    assert rel(feat, inter["features"].permute(0, 2, 3, 1)) <= 2e-2
+    theta = recognizer.tap("theta", (b, 6), torch.float32).cpu()
+    assert float((theta - inter["theta"]).abs().max()) <= 2e-2
+    warped = recognizer.tap("warped", (b, 50, 7, 512), torch.float16).float().cpu()
+    assert rel(warped, inter["warped"]) <= 5e-2               # sampling positions move with theta
+    fc9 = recognizer.tap("fc_9", (b, 50, 128), torch.float16).float().cpu()
+    assert rel(fc9, inter["fc_9"]) <= 5e-2
+    l2 = recognizer.tap("l2", (b, 50, 256), torch.float16).float().cpu()
+    assert float((l2 - inter["l2"]).abs().max()) <= 5e-2       # LSTM outputs live in [-1, 1]
+    logits = recognizer.tap("logits", (b, 48, 37), torch.float32).cpu()
+    ref_logits = inter["logits"]
+    assert float((logits - ref_logits).abs().max()) <= 0.15
+    # decoded strings: identical wherever the oracle's argmax is decided by more than the fp16 noise
+    top2 = torch.topk(ref_logits, 2, -1).values
+    decisive = bool(((top2[..., 0] - top2[..., 1]) > 0.3).all())
+    ref_texts = crnn.labels_to_text(crnn.ctc_greedy(probs))
+    if decisive:
+        assert texts == ref_texts
+    else:
+        same = sum(a == b_ for a, b_ in zip(texts, ref_texts))
+        assert same >= b - 2, (texts, ref_texts)
+
+
+def test_ctc_collapse_exact(recognizer):
+    """Greedy CTC on the device equals the oracle's collapse of the device's own logits."""
+    from oracle import crnn
+    rng = np.random.default_rng(9)
+    crops = rng.integers(0, 256, (16, 31, 200), dtype=np.uint8)
+    t = torch.from_numpy(crops).to(recognizer.device)
+    crnn_in = torch.empty((16, 200, 31), dtype=torch.float16, device=recognizer.device)
+    recognizer.ctx.crops_to_input(t.data_ptr(), 16, crnn_in.data_ptr(), _stream())
+    labels = recognizer.predict_device(crnn_in).cpu().numpy()
+    logits = recognizer.tap("logits", (16, 48, 37), torch.float32).cpu()
+    expect = crnn.ctc_greedy(torch.softmax(logits, -1))
+    assert np.array_equal(labels, expect)                      # integer work: bit-exact
+
+
+# ------------------------------------------------------------------------------- API behaviour
+def test_reference_api_contract(detector, recognizer):
+    rng = np.random.default_rng(0)
+    blank = np.full((1, 64, 96, 3), 255, np.uint8)
+    boxes = detector.detect(blank)
+    assert len(boxes) == 1
+    groups = [np.array([])]
+    assert recognizer.recognize_from_boxes(blank, groups) == [[]]
+    with pytest.raises(AssertionError):                         # recognition.py:501-503
+        recognizer.recognize_from_boxes(blank, [])

@@ -1,0 +1,93 @@
+"""CPU: the oracle reproduces the golden vectors generated from the reference itself
+(oracle/validate_against_reference.py).  These fixtures ARE the reference's outputs."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import craft, crnn, imageops
+from keras_ocr_b200 import weights as W
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def test_craft_matches_reference_torch_twin(golden_dir):
+    g = _load(golden_dir, "craft")
+    wts = W.synthetic_craft_weights(seed=3)
+    for tag in ("even", "odd"):
+        img = g[f"craft_{tag}_image"]
+        x = torch.from_numpy(np.stack([imageops.compute_input(i) for i in img])).permute(0, 3, 1, 2).contiguous()
+        with torch.no_grad():
+            mine = craft.craft_forward(wts, x).numpy()
+        # bar = the reference's own Keras-vs-torch tolerance (tests/test_pytorch_keras.py:49, decimal=4)
+        np.testing.assert_allclose(mine, g[f"craft_{tag}_scores"], atol=1e-4)
+
+
+@pytest.mark.parametrize("tag", ["grid32", "rot12", "dense", "blank", "refmaps"])
+def test_get_boxes_matches_reference(golden_dir, tag):
+    g = _load(golden_dir, "boxes")
+    boxes = imageops.get_boxes(g[f"boxes_{tag}_scores"])
+    assert [len(b) for b in boxes] == list(g[f"boxes_{tag}_counts"])
+    flat = [b.reshape(-1, 4, 2) for b in boxes if b.size]
+    if flat:
+        assert np.array_equal(np.concatenate(flat), g[f"boxes_{tag}_quads"])     # bit-exact
+    else:
+        assert g[f"boxes_{tag}_quads"].shape[0] == 0
+        assert boxes[0].shape == (0,)          # np.array([]) like reference detection.py:286
+
+
+def test_warp_box_matches_reference(golden_dir):
+    g = _load(golden_dir, "warp")
+    for q, ref in zip(g["warp_quads"], g["warp_crops"]):
+        assert np.array_equal(imageops.warp_box(g["warp_gray"], q), ref)
+
+
+@pytest.mark.parametrize("tag", ["x2", "capped", "x3"])
+def test_resize_matches_reference(golden_dir, tag):
+    g = _load(golden_dir, "inputs")
+    scale, max_size, s_ref = g[f"resize_{tag}_params"]
+    out, s = imageops.resize_image(g[f"resize_{tag}_src"], scale, max_size)
+    assert s == s_ref and np.array_equal(out, g[f"resize_{tag}_dst"])
+
+
+def test_blank_image_has_no_boxes():
+    """reference tests/test_pipeline.py:9-12 at the getBoxes level: flat maps -> zero predictions."""
+    assert imageops.get_boxes(np.zeros((1, 128, 128, 2), np.float32))[0].shape == (0,)
+
+
+def test_ctc_greedy_semantics():
+    probs = np.full((1, 6, 37), 1e-3, np.float32)
+    for t, c in enumerate([5, 5, 36, 5, 7, 7]):       # repeat, blank, repeat-after-blank, new, repeat
+        probs[0, t, c] = 0.9
+    out = crnn.ctc_greedy(probs)
+    assert out[0].tolist() == [5, 5, 7, -1, -1, -1]
+    assert crnn.labels_to_text(out) == ["557"]
+
+
+def test_crnn_oracle_shapes_and_backward_order():
+    wts = W.synthetic_crnn_weights(seed=2)
+    rng = np.random.default_rng(0)
+    crops = rng.integers(0, 256, (2, 31, 200)).astype(np.float32) / 255
+    with torch.no_grad():
+        probs, inter = crnn.crnn_logits(wts, crops, return_intermediates=True)
+    assert probs.shape == (2, 48, 37) and inter["warped"].shape == (2, 50, 7, 512)
+    np.testing.assert_allclose(probs.sum(-1).numpy(), 1.0, atol=1e-5)
+    # go_backwards keeps processing order: step 0 of the backward LSTM only saw the LAST input step
+    w = crnn._t(wts)
+    x = inter["fc_9"]
+    back = crnn.lstm(w, x, "lstm_10_back", go_backwards=True)
+    x2 = x.clone(); x2[:, :-1] = 0
+    back2 = crnn.lstm(w, x2, "lstm_10_back", go_backwards=True)
+    np.testing.assert_allclose(back[:, 0].numpy(), back2[:, 0].numpy(), atol=1e-6)
+
+
+def test_stn_sampler_quirk_zero_last_row_and_column():
+    """with identity theta the last row / column of the output is exactly 0."""
+    feat = torch.ones(1, 50, 7, 4)
+    theta = torch.tensor([[1.0, 0, 0, 0, 1.0, 0]])
+    out = crnn.stn_sample(feat, theta)
+    assert float(out[0, :, 6].abs().max()) == 0.0 and float(out[0, 49].abs().max()) == 0.0
+    np.testing.assert_allclose(out[0, :49, :6].numpy(), 1.0, atol=1e-6)
