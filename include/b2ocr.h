@@ -60,6 +60,12 @@ int b2o_set_conv_engine(b2o_ctx* ctx, int engine);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 int64_t b2o_launch_count(const b2o_ctx* ctx);
 
+/* Measurement hook (bench.py's roofline leg): when enabled, every launch of the tensor-core conv
+ * kernel is bracketed by CUDA events on its stream; b2o_profile_read sums the kernel time (ms), the
+ * algorithmic FLOPs (2*pixels*taps*cin*cout) and the launch count since b2o_profile_enable(1). */
+int b2o_profile_enable(b2o_ctx* ctx, int on);
+int b2o_profile_read(b2o_ctx* ctx, double* tc_ms, double* tc_flop, int64_t* tc_launches);
+
 /* Detector() / Recognizer() weight loading (detection.py:686-696, recognition.py:382-404).
  * Folds batch-norm, converts to fp16 and packs into the kernels' layouts on the device.      */
 int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n);

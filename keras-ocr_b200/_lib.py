@@ -35,6 +35,8 @@ SIGNATURES = {
     "b2o_last_error": (_c.c_char_p, [_vp]),
     "b2o_set_conv_engine": (_i, [_vp, _i]),
     "b2o_launch_count": (_c.c_int64, [_vp]),
+    "b2o_profile_enable": (_i, [_vp, _i]),
+    "b2o_profile_read": (_i, [_vp, _c.POINTER(_c.c_double), _c.POINTER(_c.c_double), _c.POINTER(_c.c_int64)]),
     "b2o_load_craft": (_i, [_vp, _c.POINTER(_Tensor), _i]),
     "b2o_load_crnn": (_i, [_vp, _c.POINTER(_Tensor), _i]),
     "b2o_resize_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
@@ -125,6 +127,15 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.b2o_launch_count(self.handle))
+
+    def profile_enable(self, on):
+        self._check(self.lib.b2o_profile_enable(self.handle, int(on)), "b2o_profile_enable")
+
+    def profile_read(self):
+        ms, flop, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+        self._check(self.lib.b2o_profile_read(self.handle, ctypes.byref(ms), ctypes.byref(flop), ctypes.byref(n)),
+                    "b2o_profile_read")
+        return ms.value, flop.value, n.value
 
     def load_craft(self, weights):
         arr, keep = _tensor_array(weights)

@@ -193,11 +193,36 @@ extern "C" void b2o_destroy(b2o_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   for (void* p : ctx->owned) cudaFree(p);
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
   delete ctx;
 }
 
 extern "C" const char* b2o_last_error(const b2o_ctx* ctx) { return ctx ? ctx->error.c_str() : "null context"; }
 extern "C" int64_t b2o_launch_count(const b2o_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int b2o_profile_enable(b2o_ctx* ctx, int on) {
+  if (!ctx) return B2O_ERR_ARG;
+  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  ctx->prof_events.clear();
+  ctx->prof_flop = 0.0;
+  ctx->profile = on != 0;
+  return B2O_OK;
+}
+
+extern "C" int b2o_profile_read(b2o_ctx* ctx, double* tc_ms, double* tc_flop, int64_t* tc_launches) {
+  if (!ctx || !tc_ms || !tc_flop || !tc_launches) return B2O_ERR_ARG;
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < ctx->prof_events.size(); i += 2) {
+    B2O_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->prof_events[i + 1]));
+    float t = 0.f;
+    B2O_CUDA_CHECK(ctx, cudaEventElapsedTime(&t, ctx->prof_events[i], ctx->prof_events[i + 1]));
+    ms += t;
+  }
+  *tc_ms = ms;
+  *tc_flop = ctx->prof_flop;
+  *tc_launches = static_cast<int64_t>(ctx->prof_events.size() / 2);
+  return B2O_OK;
+}
 
 extern "C" int b2o_set_conv_engine(b2o_ctx* ctx, int engine) {
   if (!ctx || (engine != B2O_CONV_AUTO && engine != B2O_CONV_SIMT)) return B2O_ERR_ARG;

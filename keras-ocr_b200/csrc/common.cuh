@@ -73,6 +73,10 @@ struct b2o_ctx {
   __half* lstm_u[4] = {nullptr, nullptr, nullptr, nullptr};    // recurrent kernels [128][512] fp16
   float *fc12_w = nullptr, *fc12_b = nullptr;                  // [256][37], [37] fp32
   std::vector<void*> owned;    // device allocations freed in b2o_destroy
+  // optional per-launch timing of the tensor-core conv kernel (bench.py's roofline leg)
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_events;   // (start, stop) pairs
+  double prof_flop = 0.0;
   void set_error(const std::string& e) { error = e; }
 };
 

@@ -422,8 +422,21 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     configured = true;
   }
   const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profile) {
+    B2O_CUDA_CHECK(ctx, cudaEventCreate(&e0));
+    B2O_CUDA_CHECK(ctx, cudaEventCreate(&e1));
+    B2O_CUDA_CHECK(ctx, cudaEventRecord(e0, st));
+  }
   conv_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(amap, L.wmap, p);
   B2O_LAUNCH_CHECK(ctx);
+  if (ctx->profile) {
+    B2O_CUDA_CHECK(ctx, cudaEventRecord(e1, st));
+    ctx->prof_events.push_back(e0);
+    ctx->prof_events.push_back(e1);
+    // algorithmic FLOPs of this launch: 2 * pixels * (taps * cin) * cout
+    ctx->prof_flop += 2.0 * double(p.N) * p.H * p.W * double(p.ksize * p.ksize) * p.cin * p.cout;
+  }
   return B2O_OK;
 }
 

@@ -45,7 +45,11 @@ class Pipeline:
         batch = torch.empty((n, hp, wp, 3), dtype=torch.uint8, device=det.device)
         same = isinstance(images, np.ndarray) and images.ndim == 4
         h2d = 0
-        if same:
+        if isinstance(images, torch.Tensor):
+            # sources already resident in HBM (bench.py's device-resident leg): no copy
+            assert images.is_cuda and images.dtype == torch.uint8 and images.dim() == 4
+            src_all, same = images.contiguous(), True
+        elif same:
             src_all = torch.from_numpy(np.ascontiguousarray(images)).pin_memory().to(det.device, non_blocking=True)
             h2d = src_all.numel()
         for i, image in enumerate(images):
@@ -66,7 +70,7 @@ class Pipeline:
         Returns a list (one entry per image) of lists of (text, box) tuples, boxes (4,2) float32 in
         the coordinates of the *input* image.
         """
-        if not isinstance(images, np.ndarray):
+        if not isinstance(images, (np.ndarray, torch.Tensor)):
             images = [tools.read(image) for image in images]
         if detection_kwargs is None:
             detection_kwargs = {}

@@ -71,8 +71,39 @@ def _he(rng, shape, fan_in, gain=2.0):
     return (rng.standard_normal(shape) * np.sqrt(gain / fan_in)).astype(np.float32)
 
 
-def synthetic_craft_weights(seed=0):
-    """Seeded CRAFT weights keyed like the reference's ``.pth`` (prefix stripped)."""
+# "textlike" routing: channel 0 carries a fine "ink" signal (strokes), channel 1 a coarse one (whole
+# words) through the layers listed here; see synthetic_craft_weights(textlike=True).
+_FINE = ["basenet.slice1.3", "basenet.slice1.7", "basenet.slice1.10"]
+_COARSE = ["basenet.slice2.14", "basenet.slice2.17", "basenet.slice3.20", "basenet.slice3.24", "basenet.slice3.27"]
+TEXTLIKE_HEAD = {"text_gain": 0.5, "text_bias": 0.0, "link_gain": 2.0, "link_bias": 0.0}   # calibrated on cv2.putText pages
+
+
+def _route(w, name, bn, out_ch, in_ch, mode, gain=1.0, bias=0.0):
+    """Make output channel ``out_ch`` of conv ``name`` depend only on input channel ``in_ch``:
+    mode "blur" = 3x3 box filter, "id" = centre tap (or the single tap of a 1x1)."""
+    k = w[name + ".weight"]
+    k[out_ch] = 0.0
+    if mode == "blur":
+        k[out_ch, in_ch] = gain / (k.shape[2] * k.shape[3])
+    else:
+        k[out_ch, in_ch, k.shape[2] // 2, k.shape[3] // 2] = gain
+    w[name + ".bias"][out_ch] = bias
+    if bn is not None:
+        w[bn + ".weight"][out_ch] = 1.0
+        w[bn + ".bias"][out_ch] = 0.0
+        w[bn + ".running_mean"][out_ch] = 0.0
+        w[bn + ".running_var"][out_ch] = 1.0
+
+
+def synthetic_craft_weights(seed=0, textlike=False):
+    """Seeded CRAFT weights keyed like the reference's ``.pth`` (prefix stripped).
+
+    ``textlike=True`` overwrites two channels per layer so that, on dark-text-on-light pages, the
+    network output is a usable (text, link) pair: text = blurred ink at half resolution, link = a
+    coarse blob per word routed through the H/8 tap and the decoder.  Every other channel keeps
+    its random weights (the arithmetic cost is unchanged); the point is that ``getBoxes`` and the
+    recognizer see realistic word boxes although no pretrained checkpoint exists offline.
+    """
     rng = np.random.default_rng(seed)
     w = {}
     for name, cin, cout, k, _dil, bn, relu in CRAFT_CONVS:
@@ -84,6 +115,31 @@ def synthetic_craft_weights(seed=0):
             w[bn + ".bias"] = (rng.standard_normal(cout) * 0.1).astype(np.float32)
             w[bn + ".running_mean"] = (rng.standard_normal(cout) * 0.1).astype(np.float32)
             w[bn + ".running_var"] = rng.uniform(0.8, 1.25, cout).astype(np.float32)
+    if textlike:
+        bn_of = {name: bn for name, _ci, _co, _k, _d, bn, _r in CRAFT_CONVS}
+        # ink = relu(1 - mean(normalised RGB)): 0 on white, ~2.3 on dark strokes
+        k = w["basenet.slice1.0.weight"]
+        k[0] = 0.0
+        k[0, :, 1, 1] = -1.0 / 3.0
+        w["basenet.slice1.0.bias"][0] = 1.0
+        for key, val in ((".weight", 1.0), (".bias", 0.0), (".running_mean", 0.0), (".running_var", 1.0)):
+            w["basenet.slice1.1" + key][0] = val
+        for name in _FINE + _COARSE:
+            _route(w, name, bn_of[name], 0, 0, "blur")
+        _route(w, "upconv2.conv.0", "upconv2.conv.1", 1, 256, "id")       # concat [y1(256), s3(512)] -> s3 ch0
+        _route(w, "upconv2.conv.3", "upconv2.conv.4", 1, 1, "blur")
+        _route(w, "upconv3.conv.0", "upconv3.conv.1", 1, 1, "id")         # concat [y2(128), s2(256)] -> y2 ch1
+        _route(w, "upconv3.conv.3", "upconv3.conv.4", 1, 1, "blur")
+        _route(w, "upconv4.conv.0", "upconv4.conv.1", 0, 64, "id")        # concat [y3(64), s1(128)] -> s1 ch0
+        _route(w, "upconv4.conv.0", "upconv4.conv.1", 1, 1, "id")         #                          -> y3 ch1
+        _route(w, "upconv4.conv.3", "upconv4.conv.4", 0, 0, "id")
+        _route(w, "upconv4.conv.3", "upconv4.conv.4", 1, 1, "blur")
+        for name in ("conv_cls.0", "conv_cls.2", "conv_cls.4", "conv_cls.6"):
+            _route(w, name, None, 0, 0, "id")
+            _route(w, name, None, 1, 1, "id")
+        h = TEXTLIKE_HEAD
+        _route(w, "conv_cls.8", None, 0, 0, "id", h["text_gain"], h["text_bias"])
+        _route(w, "conv_cls.8", None, 1, 1, "id", h["link_gain"], h["link_bias"])
     return w
 
 

@@ -278,3 +278,49 @@ def test_reference_api_contract(detector, recognizer):
     assert recognizer.recognize_from_boxes(blank, groups) == [[]]
     with pytest.raises(AssertionError):                         # recognition.py:501-503
         recognizer.recognize_from_boxes(blank, [])
+
+
+# ------------------------------------------------------------------------------- end to end
+def test_pipeline_recognize_vs_oracle_chain(cuda_device):
+    """Whole Pipeline.recognize on rendered pages, fp16 GPU chain vs fp32 oracle chain.
+    Tolerance (chained): same box count and order, corners within 2 px at
+    detector-input scale (= 1 px in source pixels at scale 2), decoded strings mostly identical
+    (random CRNN weights leave some near-tie argmaxes that fp16 may flip)."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import synth
+    from oracle.pipeline import OraclePipeline
+
+    cw, rw = W.synthetic_craft_weights(3, textlike=True), W.synthetic_crnn_weights(2)
+    pages, _ = synth.text_images(seed=21, n=2, h=192, w=384, n_words=4)
+    pipe = Pipeline(detector=Detector(weights=cw), recognizer=Recognizer(weights=rw), scale=2)
+    got = pipe.recognize(pages)
+    ref = OraclePipeline(cw, rw, scale=2).recognize(pages)
+    assert [len(g) for g in got] == [len(r) for r in ref]
+    assert sum(len(r) for r in ref) >= 6                        # the synthetic pages really produce word boxes
+    worst, same, total = 0.0, 0, 0
+    for g, r in zip(got, ref):
+        for (tg, bg), (tr, br) in zip(g, r):
+            assert bg.shape == (4, 2) and bg.dtype == np.float32
+            worst = max(worst, _match_quads(bg, br))
+            same += int(tg == tr)
+            total += 1
+    assert worst <= 1.0, worst                                  # source-image pixels (scale 2)
+    assert same >= 0.6 * total, (same, total)
+    # same call with a list input and with device-resident sources gives the same result
+    again = pipe.recognize([p for p in pages])
+    assert [[t for t, _ in g] for g in again] == [[t for t, _ in g] for g in got]
+    dev = pipe.recognize(torch.from_numpy(pages).to(cuda_device))
+    assert [[t for t, _ in g] for g in dev] == [[t for t, _ in g] for g in got]
+
+
+def test_blank_page_gives_no_predictions(cuda_device):
+    """reference tests/test_pipeline.py:9-12 (blank image -> zero predictions)."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    pipe = Pipeline(detector=Detector(weights=W.synthetic_craft_weights(3, textlike=True)),
+                    recognizer=Recognizer(weights=W.synthetic_crnn_weights(2)), scale=2)
+    out = pipe.recognize([np.full((256, 256, 3), 255, np.uint8)])
+    assert out == [[]]
