@@ -50,7 +50,7 @@ typedef struct {
 
 /* Which convolution engine to use: B2O_CONV_AUTO = tcgen05 wherever the shape allows (the product
  * path), B2O_CONV_SIMT = CUDA-core debug engine used to cross-check the tcgen05 kernels.      */
-enum { B2O_CONV_AUTO = 0, B2O_CONV_SIMT = 1 };
+enum { B2O_CONV_AUTO = 0, B2O_CONV_SIMT = 1, B2O_CONV_TC_GENERIC = 2 /* tcgen05 without halo tiles / fused pool */ };
 
 int b2o_version(void);
 int b2o_create(int device, b2o_ctx** out);

@@ -12,7 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ocr.so")
 
-CONV_AUTO, CONV_SIMT = 0, 1
+CONV_AUTO, CONV_SIMT, CONV_TC_GENERIC = 0, 1, 2
 
 
 class B2OError(RuntimeError):

@@ -225,7 +225,7 @@ extern "C" int b2o_profile_read(b2o_ctx* ctx, double* tc_ms, double* tc_flop, in
 }
 
 extern "C" int b2o_set_conv_engine(b2o_ctx* ctx, int engine) {
-  if (!ctx || (engine != B2O_CONV_AUTO && engine != B2O_CONV_SIMT)) return B2O_ERR_ARG;
+  if (!ctx || (engine != B2O_CONV_AUTO && engine != B2O_CONV_SIMT && engine != B2O_CONV_TC_GENERIC)) return B2O_ERR_ARG;
   ctx->conv_engine = engine;
   return B2O_OK;
 }
@@ -405,19 +405,15 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
 
   // encoder (detection.py:312-324); taps s1..s4 are written straight into the concat buffers
   B2O_RETURN_IF(stem_rgb_run(ctx, L("basenet.slice1.0"), img, n, h, w, a, st));
-  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.3"), a, b, 0, st));
-  B2O_RETURN_IF(maxpool2_run(ctx, b, p1, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.3"), a, b, 0, st, &p1, 0));     // conv + fused 2x2 max pool
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.7"), p1, c, 0, st));
-  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.10"), c, s1, 0, st));
-  B2O_RETURN_IF(maxpool2_run(ctx, s1, p2, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.10"), c, s1, 0, st, &p2, 1));   // tap s1 (full) + pooled
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice2.14"), p2, d, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice2.17"), d, s2, 0, st));
-  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice3.20"), s2, e, 0, st));
-  B2O_RETURN_IF(maxpool2_run(ctx, e, p3, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice3.20"), s2, e, 0, st, &p3, 0));
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice3.24"), p3, f, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice3.27"), f, s3, 0, st));
-  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice4.30"), s3, g, 0, st));
-  B2O_RETURN_IF(maxpool2_run(ctx, g, p4, st));
+  B2O_RETURN_IF(conv_run(ctx, L("basenet.slice4.30"), s3, g, 0, st, &p4, 0));
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice4.34"), p4, hh, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice4.37"), hh, s4, 0, st));          // BN only, no ReLU (333)
   // slice5 (365-378)
@@ -466,16 +462,14 @@ extern "C" int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in, int b, int32_
   // conv stack (recognition.py:217-242)
   B2O_RETURN_IF(stem_crnn_run(ctx, L("conv_1"), reinterpret_cast<const __half*>(crnn_in), b, x1, st));
   B2O_RETURN_IF(conv_run(ctx, L("conv_2"), x1, x2, 0, st));
-  B2O_RETURN_IF(conv_run(ctx, L("conv_3"), x2, x3, 0, st));
-  B2O_RETURN_IF(maxpool2_run(ctx, x3, p3, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_3"), x2, x3, 0, st, &p3, 0));
   B2O_RETURN_IF(conv_run(ctx, L("conv_4"), p3, x4, 0, st));
-  B2O_RETURN_IF(conv_run(ctx, L("conv_5"), x4, x5, 0, st));
-  B2O_RETURN_IF(maxpool2_run(ctx, x5, p5, st));
+  B2O_RETURN_IF(conv_run(ctx, L("conv_5"), x4, x5, 0, st, &p5, 0));
   B2O_RETURN_IF(conv_run(ctx, L("conv_6"), p5, x6, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("conv_7"), x6, x7, 0, st));
   // spatial transformer (263-281)
   B2O_RETURN_IF(conv_run(ctx, L("stn.conv_a"), x7, sa, 0, st));
-  B2O_RETURN_IF(conv_simt_run(ctx, L("stn.conv_b"), sa, sb, 0, st));
+  B2O_RETURN_IF(conv_run(ctx, L("stn.conv_b"), sa, sb, 0, st));
   const TensorView sb_flat = make_view(base + p.off_sb, 1, 1, b, 11200), d1 = make_view(base + p.off_d1, 1, 1, b, 64);
   B2O_RETURN_IF(conv_run(ctx, L("stn.dense_a"), sb_flat, d1, 0, st));
   float* theta = reinterpret_cast<float*>(base + p.off_theta);
@@ -544,8 +538,11 @@ extern "C" int b2o_conv2d_test(b2o_ctx* ctx, const void* x, int n, int h, int w,
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (rc == B2O_OK) {
     const TensorView in = make_view(const_cast<void*>(x), n, h, w, cin), o = make_view(out, n, h, w, cout);
+    const int saved = ctx->conv_engine;
+    ctx->conv_engine = engine;
     if (engine == B2O_CONV_SIMT) rc = conv_simt_run(ctx, L, in, o, 0, st);
     else rc = conv_tc_run(ctx, L, in, o, 0, st);
+    ctx->conv_engine = saved;
   }
   cudaError_t e = cudaStreamSynchronize(st);
   if (rc == B2O_OK && e != cudaSuccess) { ctx->set_error(std::string("conv2d_test: ") + cudaGetErrorString(e)); rc = B2O_ERR_CUDA; }

@@ -52,6 +52,7 @@ struct ConvLayer {
   float *s1 = nullptr, *t1 = nullptr, *s2 = nullptr, *t2 = nullptr;
   CUtensorMap wmap;            // TMA map over w_kmajor (box 64 x block_n)
   int block_n = 0;             // tcgen05 N tile; 0 = layer not eligible for the tensor-core engine
+  int kch = 0;                 // tcgen05 K chunk (channels per stage): 64 / 32 / 16
 };
 
 struct TensorView {            // NHWC fp16 activation living inside a (possibly wider) buffer
@@ -82,12 +83,13 @@ struct b2o_ctx {
 
 // ---- engines (conv_tc.cu, conv_simt.cu) -------------------------------------------------------
 int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L);   // builds wmap / picks block_n (0 if ineligible)
+// pool_out != null: also write the 2x2/2 max-pooled output (fused epilogue); write_full = 0 skips `out`
 int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
-                int out_f32, cudaStream_t st);
+                int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1);
 int conv_simt_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
                   int out_f32, cudaStream_t st);
 int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
-             int out_f32, cudaStream_t st);
+             int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1);
 int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, int h, int w,
                  const TensorView& out, cudaStream_t st);
 int stem_crnn_run(b2o_ctx* ctx, const ConvLayer& L, const __half* x, int b, const TensorView& out,

@@ -351,9 +351,17 @@ int conv_simt_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const 
 }
 
 int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out, int out_f32,
-             cudaStream_t st) {
-  if (ctx->conv_engine == B2O_CONV_AUTO && L.block_n != 0) return conv_tc_run(ctx, L, in, out, out_f32, st);
-  return conv_simt_run(ctx, L, in, out, out_f32, st);
+             cudaStream_t st, const TensorView* pool_out, int write_full) {
+  if (ctx->conv_engine != B2O_CONV_SIMT && L.block_n != 0) {
+    if (pool_out != nullptr && (ctx->conv_engine == B2O_CONV_TC_GENERIC)) {      // generic tiles: unfused pool
+      B2O_RETURN_IF(conv_tc_run(ctx, L, in, out, out_f32, st));
+      return maxpool2_run(ctx, out, *pool_out, st);
+    }
+    return conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full);
+  }
+  B2O_RETURN_IF(conv_simt_run(ctx, L, in, out, out_f32, st));
+  if (pool_out != nullptr) return maxpool2_run(ctx, out, *pool_out, st);
+  return B2O_OK;
 }
 
 int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, int h, int w, const TensorView& out,

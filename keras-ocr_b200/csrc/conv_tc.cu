@@ -5,28 +5,33 @@
 //
 //   D[pixel, cout] = sum_{tap, c} X[pixel + offset(tap), c] * Wt[cout, tap, c]
 //
-// * M = 128 output pixels per tile, chosen as a (BW x BH x BNI) box of the NHWC activation so one
-//   4-D TMA load per (tap, 64-channel chunk) fetches the shifted A tile; TMA's out-of-bounds
-//   zero fill implements "same" padding and dilation for free.
-// * B = weights packed K-major [cout][tap*cin + c], loaded with a 2-D TMA box (64 x BLOCK_N).
-// * both operands land in 128B-swizzled shared memory; one elected thread issues
-//   tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16) x4 per stage; fp32 accumulators
-//   live in TMEM (2 stages) so the epilogue of tile i overlaps the main loop of tile i+1.
-// * warp roles: warp0 = TMA producer, warp1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue
-//   (tcgen05.ld -> scale/shift/ReLU/affine -> fp16 or fp32 NHWC stores, optionally into a channel
-//   slice of a wider concat buffer).
-// * persistent: grid = min(#tiles, #SMs); tiles are walked n-tile fastest so the CTAs that share
-//   an A tile run concurrently and hit L2.
+// * M = 128 output pixels per tile = a box of the NHWC activation, so TMA fetches the A operand
+//   straight from the feature map; out-of-bounds zero fill implements "same" padding / dilation.
+//   - generic mode: one 4-D TMA box (KCH, BW, BH, BNI) per (tap, channel chunk), any k / dilation;
+//   - halo mode (3x3, dilation 1): the tile is 8 (w) x 16 (h); ONE box of 8 x 18 rows per
+//     (dx, channel chunk) serves the three dy taps, whose A descriptors are the same stage shifted
+//     by whole 8-pixel rows (a multiple of the swizzle period) -- 3x less L2->SM traffic.
+// * B = weights packed K-major [cout][tap*cin + c], 2-D TMA boxes (KCH x BLOCK_N); when the whole
+//   filter bank fits in shared memory (small layers) it is loaded once per CTA and stays resident.
+// * K chunk KCH = 64 / 32 / 16 channels (128B / 64B / 32B swizzle) so 32- and 16-channel layers
+//   (CRAFT conv_cls.*, STN) also run on the tensor cores.
+// * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16); fp32
+//   accumulators live in TMEM (2 stages): the epilogue of tile i overlaps the main loop of tile i+1.
+// * warp roles: warp0 = TMA producer (A ring + B ring), warp1 = TMEM allocator + MMA issuer,
+//   warps 2..5 = epilogue: tcgen05.ld -> scale/shift/ReLU/affine -> fp16|fp32 NHWC stores (possibly
+//   into a channel slice of a concat buffer) and, optionally, the fused 2x2 max-pool output.
+// * persistent: grid = min(#tiles, #SMs); n-tiles of one pixel tile run back to back.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;               // fp16 elements per stage along K (= 128 B swizzle span)
 constexpr int UMMA_K = 16;
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K * 2;
 constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int SMEM_TOTAL = 230 * 1024;     // dynamic shared memory we allow ourselves (max 227 KB = 232448 B)
+constexpr int MAX_RING = 8;
 
 struct TcParams {
   int N, H, W;
@@ -35,11 +40,16 @@ struct TcParams {
   int tiles_w, tiles_h, tiles_n;          // M-tile grid
   int n_tiles;                            // cout / BLOCK_N
   int total_tiles;
+  int halo, resident;
+  int na, nb;                             // ring depths
+  int a_stride, a_bytes;                  // bytes between A stages / bytes one A box delivers
+  int off_b, off_bar;                     // shared-memory offsets
   const float *s1, *t1, *s2, *t2;
   int relu;
   void* out;
-  int out_ld;
-  int out_f32;
+  int out_ld, out_f32, write_full;
+  __half* pool_out;                       // fused 2x2/2 max-pool output (or null)
+  int pool_ld, PH, PW;
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -81,9 +91,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void fence_proxy_async() {
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-}
 __device__ __forceinline__ void tcgen05_before_sync() {
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -108,14 +115,17 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (rows of 128 B, 8-row atoms 1024 B apart).
+// K-major swizzled shared-memory matrix descriptor: rows of KCH*2 bytes, 8-row atoms SBO bytes apart.
+template <int KCH>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
+  constexpr uint64_t SBO = 16 * KCH;                       // 8 rows x (KCH*2) bytes
+  constexpr uint64_t LAYOUT = KCH == 64 ? 2 : (KCH == 32 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
   uint64_t d = 0;
-  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);   // start address      bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                    // leading byte off.  bits [16,30) (unused here)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;            // stride byte offset bits [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                    // descriptor version bits [46,48)
-  d |= static_cast<uint64_t>(2) << 61;                    // SWIZZLE_128B       bits [61,64)
+  d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);    // start address      bits [0,14)
+  d |= static_cast<uint64_t>(1) << 16;                     // leading byte off.  bits [16,30) (unused: swizzled K-major)
+  d |= (SBO >> 4) << 32;                                   // stride byte offset bits [32,46)
+  d |= static_cast<uint64_t>(1) << 46;                     // descriptor version bits [46,48)
+  d |= LAYOUT << 61;                                       // swizzle mode       bits [61,64)
   return d;
 }
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -158,33 +168,39 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
-template <int BLOCK_N>
-struct TcConfig {
-  static constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
-  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int CH = BLOCK_N >= 32 ? 32 : 16;     // accumulator columns per tcgen05.ld
-};
+struct TileCoord { int w0, h0, n0, n_tile; };
+__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;
+  const int m_tile = tile / p.n_tiles;
+  t.w0 = (m_tile % p.tiles_w) << p.bw_log2;
+  t.h0 = ((m_tile / p.tiles_w) % p.tiles_h) << p.bh_log2;
+  t.n0 = (m_tile / (p.tiles_w * p.tiles_h)) << p.bn_log2;
+  return t;
+}
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int BLOCK_N>
+template <int BLOCK_N, int KCH>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                const TcParams p) {
-  using Cfg = TcConfig<BLOCK_N>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr int B_BYTES = BLOCK_N * KCH * 2;
+  constexpr int TAP_SHIFT = 16 * KCH;                      // bytes of one 8-pixel row group (= SBO)
+  constexpr int KSTEPS = KCH / UMMA_K;
+  constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
+  constexpr int CH = BLOCK_N >= 32 ? 32 : 16;              // accumulator columns per tcgen05.ld
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
+  uint8_t* smem_b = smem + p.off_b;
+  uint64_t* a_full = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint64_t* a_empty = a_full + MAX_RING;
+  uint64_t* b_full = a_empty + MAX_RING;
+  uint64_t* b_empty = b_full + MAX_RING;
+  uint64_t* tmem_full = b_empty + MAX_RING;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -192,19 +208,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&amap);
     tma_prefetch_desc(&bmap);
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+    for (int s = 0; s < MAX_RING; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], 128);
     }
+    mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(Cfg::TMEM_COLS)
+                 "r"(TMEM_COLS)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -214,32 +233,41 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   const uint32_t tmem_base = *tmem_slot;
 
   const int taps = p.ksize * p.ksize;
-  const int kchunks = p.cin / BLOCK_K;
-  const int k_iters = taps * kchunks;
+  const int kchunks = p.cin / KCH;
   const int half_k = p.ksize >> 1;
+  const int n_a = (p.halo ? 3 : taps) * kchunks;           // A stages per tile
+  const int taps_per_a = p.halo ? 3 : 1;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
+      if (p.resident) {                                    // whole filter bank, once per CTA
+        mbar_expect_tx(res_full, static_cast<uint32_t>(taps * kchunks * B_BYTES));
+        for (int tap = 0; tap < taps; ++tap)
+          for (int kc = 0; kc < kchunks; ++kc)
+            tma_load_2d(&bmap, res_full, smem_b + (tap * kchunks + kc) * B_BYTES, tap * p.cin + kc * KCH, 0);
+      }
+      int sa = 0, sb = 0;
+      uint32_t pa = 0, pb = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
-        const int tw = m_tile % p.tiles_w;
-        const int th = (m_tile / p.tiles_w) % p.tiles_h;
-        const int tn = m_tile / (p.tiles_w * p.tiles_h);
-        const int w0 = tw << p.bw_log2, h0 = th << p.bh_log2, n0 = tn << p.bn_log2;
-        for (int tap = 0; tap < taps; ++tap) {
-          const int dy = (tap / p.ksize - half_k) * p.dil;
-          const int dx = (tap % p.ksize - half_k) * p.dil;
-          for (int kc = 0; kc < kchunks; ++kc) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-            tma_load_4d(&amap, &full_bar[stage], smem_a + stage * A_STAGE_BYTES, kc * BLOCK_K, w0 + dx, h0 + dy, n0);
-            tma_load_2d(&bmap, &full_bar[stage], smem_b + stage * Cfg::B_STAGE_BYTES, tap * p.cin + kc * BLOCK_K,
-                        n_tile * BLOCK_N);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        const TileCoord tc = tile_coord(p, tile);
+        for (int it = 0; it < n_a; ++it) {
+          const int g = it / kchunks, kc = it - g * kchunks;   // g = dx index (halo) or tap (generic)
+          int ax, ay;
+          if (p.halo) { ax = tc.w0 + g - 1; ay = tc.h0 - 1; }
+          else { ax = tc.w0 + (g % p.ksize - half_k) * p.dil; ay = tc.h0 + (g / p.ksize - half_k) * p.dil; }
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(p.a_bytes));
+          tma_load_4d(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tc.n0);
+          if (++sa == p.na) { sa = 0; pa ^= 1; }
+          if (!p.resident) {
+            for (int t = 0; t < taps_per_a; ++t) {
+              const int tap = p.halo ? (t * 3 + g) : g;
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              mbar_expect_tx(&b_full[sb], B_BYTES);
+              tma_load_2d(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, tc.n_tile * BLOCK_N);
+              if (++sb == p.nb) { sb = 0; pb ^= 1; }
+            }
           }
         }
       }
@@ -250,35 +278,53 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       // instruction descriptor: D=f32, A=B=f16, both K-major, N=BLOCK_N, M=128
       constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                  (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
+      if (p.resident) { mbar_wait(res_full, 0); tcgen05_after_sync(); }
+      int sa = 0, sb = 0, acc = 0;
+      uint32_t pa = 0, pb = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_after_sync();
         const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        for (int it = 0; it < k_iters; ++it) {
-          mbar_wait(&full_bar[stage], phase);
+        uint32_t accumulate = 0;
+        for (int it = 0; it < n_a; ++it) {
+          const int g = it / kchunks, kc = it - g * kchunks;
+          mbar_wait(&a_full[sa], pa);
           tcgen05_after_sync();
-          const uint64_t adesc = umma_desc(smem_u32(smem_a + stage * A_STAGE_BYTES));
-          const uint64_t bdesc = umma_desc(smem_u32(smem_b + stage * Cfg::B_STAGE_BYTES));
+          const uint32_t a_base = smem_u32(smem_a + sa * p.a_stride);
+          for (int t = 0; t < taps_per_a; ++t) {
+            uint32_t b_addr;
+            if (p.resident) {
+              const int tap = p.halo ? (t * 3 + g) : g;
+              b_addr = smem_u32(smem_b + (tap * kchunks + kc) * B_BYTES);
+            } else {
+              mbar_wait(&b_full[sb], pb);
+              tcgen05_after_sync();
+              b_addr = smem_u32(smem_b + sb * B_BYTES);
+            }
+            // dy tap t of a halo stage = the same stage shifted by t rows of 8 pixels
+            const uint64_t adesc = umma_desc<KCH>(a_base + static_cast<uint32_t>(t * TAP_SHIFT));
+            const uint64_t bdesc = umma_desc<KCH>(b_addr);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
-            umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                     (it | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < KSTEPS; ++k) {
+              // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
+              umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                       accumulate);
+              accumulate = 1;
+            }
+            if (!p.resident) {
+              umma_commit(&b_empty[sb]);
+              if (++sb == p.nb) { sb = 0; pb ^= 1; }
+            }
           }
-          umma_commit(&empty_bar[stage]);                 // frees the smem slot when the MMAs retire
-          if (it == k_iters - 1) umma_commit(&tmem_full[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          umma_commit(&a_empty[sa]);                      // frees the A slot when its MMAs retire
+          if (++sa == p.na) { sa = 0; pa ^= 1; }
         }
+        umma_commit(&tmem_full[acc]);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
-    constexpr int CH = Cfg::CH;
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may touch
     const int row = quad * 32 + lane;                     // accumulator row = pixel inside the tile
     const int bw_mask = (1 << p.bw_log2) - 1, bh_mask = (1 << p.bh_log2) - 1;
@@ -288,15 +334,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
-      const int tw = m_tile % p.tiles_w;
-      const int th = (m_tile / p.tiles_w) % p.tiles_h;
-      const int tn = m_tile / (p.tiles_w * p.tiles_h);
-      const int w = (tw << p.bw_log2) + wi, h = (th << p.bh_log2) + hi, n = (tn << p.bn_log2) + ni;
+      const TileCoord tc = tile_coord(p, tile);
+      const int w = tc.w0 + wi, h = tc.h0 + hi, n = tc.n0 + ni;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
-      const int c_base = n_tile * BLOCK_N;
+      const int c_base = tc.n_tile * BLOCK_N;
+      // fused 2x2/2 max pool (halo tiles: lane^1 = w neighbour, lane^8 = h neighbour)
+      const bool pool_writer = p.pool_out != nullptr && !(w & 1) && !(h & 1) && (w >> 1) < p.PW && (h >> 1) < p.PH &&
+                               n < p.N;
+      const size_t ppix = (static_cast<size_t>(n) * p.PH + (h >> 1)) * p.PW + (w >> 1);
 
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_after_sync();
@@ -332,26 +378,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             y[j + 3] = fmaf(y[j + 3], a.w, b.w);
           }
         }
-        if (valid) {
-          if (p.out_f32) {
+        if (p.out_f32) {
+          if (valid) {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + c0;
 #pragma unroll
             for (int j = 0; j < CH; j += 4)
               *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
-          } else {
+          }
+        } else {
+          uint32_t pk[CH / 2];
+#pragma unroll
+          for (int j = 0; j < CH; j += 2) {
+            __half2 hv = __floats2half2_rn(y[j], y[j + 1]);
+            pk[j / 2] = *reinterpret_cast<uint32_t*>(&hv);
+          }
+          if (valid && p.write_full) {
             __half* o = reinterpret_cast<__half*>(p.out) + pix * p.out_ld + c0;
 #pragma unroll
-            for (int j = 0; j < CH; j += 8) {
-              __half2 h0 = __floats2half2_rn(y[j + 0], y[j + 1]);
-              __half2 h1 = __floats2half2_rn(y[j + 2], y[j + 3]);
-              __half2 h2 = __floats2half2_rn(y[j + 4], y[j + 5]);
-              __half2 h3 = __floats2half2_rn(y[j + 6], y[j + 7]);
-              uint4 pk;
-              pk.x = *reinterpret_cast<uint32_t*>(&h0);
-              pk.y = *reinterpret_cast<uint32_t*>(&h1);
-              pk.z = *reinterpret_cast<uint32_t*>(&h2);
-              pk.w = *reinterpret_cast<uint32_t*>(&h3);
-              *reinterpret_cast<uint4*>(o + j) = pk;
+            for (int j = 0; j < CH / 2; j += 4)
+              *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+          }
+          if (p.pool_out != nullptr) {                    // warp-uniform branch
+#pragma unroll
+            for (int j = 0; j < CH / 2; ++j) {
+              __half2 m = *reinterpret_cast<__half2*>(&pk[j]);
+              uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+              m = __hmax2(m, *reinterpret_cast<__half2*>(&o1));
+              uint32_t mm = *reinterpret_cast<uint32_t*>(&m);
+              uint32_t o2 = __shfl_xor_sync(0xffffffffu, mm, 8);
+              m = __hmax2(m, *reinterpret_cast<__half2*>(&o2));
+              pk[j] = *reinterpret_cast<uint32_t*>(&m);
+            }
+            if (pool_writer) {
+              __half* o = p.pool_out + ppix * p.pool_ld + c0;
+#pragma unroll
+              for (int j = 0; j < CH / 2; j += 4)
+                *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
             }
           }
         }
@@ -366,7 +428,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   __syncthreads();
   if (warp == 1) {
     tcgen05_after_sync();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS)
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
                  : "memory");
   }
 }
@@ -388,15 +450,13 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-int ilog2(int v) {
-  int l = 0;
-  while ((1 << l) < v) ++l;
-  return l;
+CUtensorMapSwizzle swizzle_for(int kch) {
+  return kch == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kch == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
 // Pick the (bw, bh, bn) power-of-two box with bw*bh*bn = 128 that wastes the fewest pixels.
-void pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
-  double best = 1e30;
+double pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
+  double best = 1e30, best_cover = 0;
   int b_w = 7, b_h = 0, b_n = 0;
   for (int lw = 0; lw <= 7; ++lw)
     for (int lh = 0; lw + lh <= 7; ++lh) {
@@ -407,18 +467,19 @@ void pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
                            double((N + bn - 1) / bn * bn);
       // prefer wide rows (coalesced stores / fewer TMA rows) on ties; keep bw >= 8 when W allows
       const double score = cover * (1.0 + 0.001 * (7 - lw)) * ((bw < 8 && W >= 8) ? 1.05 : 1.0);
-      if (score < best) { best = score; b_w = lw; b_h = lh; b_n = ln; }
+      if (score < best) { best = score; best_cover = cover; b_w = lw; b_h = lh; b_n = ln; }
     }
   *bw_l = b_w; *bh_l = b_h; *bn_l = b_n;
+  return best_cover;
 }
 
-template <int BLOCK_N>
-int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, cudaStream_t st) {
-  using Cfg = TcConfig<BLOCK_N>;
+template <int BLOCK_N, int KCH>
+int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, int smem_bytes,
+           cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::SMEM_BYTES));
+    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             232448));
     configured = true;
   }
   const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
@@ -428,7 +489,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     B2O_CUDA_CHECK(ctx, cudaEventCreate(&e1));
     B2O_CUDA_CHECK(ctx, cudaEventRecord(e0, st));
   }
-  conv_tc_kernel<BLOCK_N><<<grid, NUM_THREADS, Cfg::SMEM_BYTES, st>>>(amap, L.wmap, p);
+  conv_tc_kernel<BLOCK_N, KCH><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
   B2O_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
     B2O_CUDA_CHECK(ctx, cudaEventRecord(e1, st));
@@ -444,19 +505,22 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
 
 int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
   L.block_n = 0;
-  if (L.cin % BLOCK_K != 0 || L.cout % 16 != 0) return B2O_OK;   // handled by the SIMT engine
+  L.kch = L.cin % 64 == 0 ? 64 : (L.cin % 32 == 0 ? 32 : (L.cin % 16 == 0 ? 16 : 0));
+  if (L.kch == 0 || L.cout % 16 != 0) return B2O_OK;      // handled by the SIMT engine
   int bn = 256;
   while (bn > 16 && (L.cout % bn != 0)) bn >>= 1;
   if (L.cout % bn != 0) return B2O_OK;
+  if (L.kch == 32 && bn > 32) return B2O_OK;               // instantiated combinations only
+  if (L.kch == 16 && bn != 32) return B2O_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return B2O_ERR_CUDA; }
   const cuuint64_t ktot = static_cast<cuuint64_t>(L.ksize) * L.ksize * L.cin;
   cuuint64_t dims[2] = {ktot, static_cast<cuuint64_t>(L.cout)};
   cuuint64_t strides[1] = {ktot * 2};
-  cuuint32_t box[2] = {BLOCK_K, static_cast<cuuint32_t>(bn)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(L.kch), static_cast<cuuint32_t>(bn)};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(&L.wmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.w_kmajor, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(L.kch), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     ctx->set_error("cuTensorMapEncodeTiled(weights " + L.name + ") failed: " + std::to_string(static_cast<int>(r)));
@@ -467,7 +531,7 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
 }
 
 int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out, int out_f32,
-                cudaStream_t st) {
+                cudaStream_t st, const TensorView* pool_out, int write_full) {
   if (L.block_n == 0) { ctx->set_error("conv_tc_run: layer " + L.name + " not eligible"); return B2O_ERR_ARG; }
   if (in.c != L.cin || out.c != L.cout || in.n != out.n || in.h != out.h || in.w != out.w) {
     ctx->set_error("conv_tc_run: shape mismatch in " + L.name);
@@ -480,43 +544,90 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   }
   EncodeTiledFn enc = get_encode();
   if (!enc) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return B2O_ERR_CUDA; }
+  const int kch = L.kch, bn = L.block_n;
+  const int taps = L.ksize * L.ksize, kchunks = L.cin / kch;
+  const int b_bytes = bn * kch * 2;
 
   TcParams p;
+  memset(&p, 0, sizeof(p));
   p.N = in.n; p.H = in.h; p.W = in.w;
   p.cin = L.cin; p.cout = L.cout; p.ksize = L.ksize; p.dil = L.dil;
-  pick_box(in.n, in.h, in.w, &p.bw_log2, &p.bh_log2, &p.bn_log2);
+  const double generic_cover = pick_box(in.n, in.h, in.w, &p.bw_log2, &p.bh_log2, &p.bn_log2);
+  // halo mode: 3x3, dilation 1, fixed 8 x 16 tile; skip it when that tile wastes >15 % more pixels
+  const double halo_cover = double((in.w + 7) / 8 * 8) * double((in.h + 15) / 16 * 16) * in.n;
+  const bool want_pool = pool_out != nullptr;
+  p.halo = (L.ksize == 3 && L.dil == 1 && ctx->conv_engine != B2O_CONV_TC_GENERIC &&
+            (halo_cover <= 1.15 * generic_cover || want_pool)) ? 1 : 0;
+  if (want_pool && !p.halo) { ctx->set_error("conv_tc_run: fused pool needs the halo tile (" + L.name + ")"); return B2O_ERR_ARG; }
+  if (p.halo) { p.bw_log2 = 3; p.bh_log2 = 4; p.bn_log2 = 0; }
   p.tiles_w = (in.w + (1 << p.bw_log2) - 1) >> p.bw_log2;
   p.tiles_h = (in.h + (1 << p.bh_log2) - 1) >> p.bh_log2;
   p.tiles_n = (in.n + (1 << p.bn_log2) - 1) >> p.bn_log2;
-  p.n_tiles = L.cout / L.block_n;
+  p.n_tiles = L.cout / bn;
   const long long total = static_cast<long long>(p.tiles_w) * p.tiles_h * p.tiles_n * p.n_tiles;
   if (total > 0x7fffffffLL) { ctx->set_error("conv_tc_run: too many tiles"); return B2O_ERR_ARG; }
   p.total_tiles = static_cast<int>(total);
+
+  // shared-memory plan: [A ring][B ring | resident filter bank][barriers]
+  const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/;
+  p.a_bytes = p.halo ? 18 * 8 * kch * 2 : 128 * kch * 2;
+  p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
+  const long long res_bytes = static_cast<long long>(taps) * kchunks * b_bytes;
+  p.resident = (p.halo && p.n_tiles == 1 && res_bytes + 2LL * p.a_stride <= budget && res_bytes <= (1 << 20) - 1) ? 1 : 0;
+  if (p.resident) {
+    p.na = static_cast<int>((budget - res_bytes) / p.a_stride);
+    if (p.na > MAX_RING) p.na = MAX_RING;
+    p.nb = 1;
+    p.off_b = p.na * p.a_stride;
+    p.off_bar = p.off_b + static_cast<int>((res_bytes + 1023) / 1024 * 1024);
+  } else if (p.halo) {
+    p.na = b_bytes <= 16384 ? 4 : 3;
+    p.nb = (budget - p.na * p.a_stride) / b_bytes;
+    if (p.nb > MAX_RING) p.nb = MAX_RING;
+    p.off_b = p.na * p.a_stride;
+    p.off_bar = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
+  } else {
+    int s = budget / (p.a_stride + b_bytes);
+    if (s > MAX_RING) s = MAX_RING;
+    p.na = p.nb = s;
+    p.off_b = p.na * p.a_stride;
+    p.off_bar = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
+  }
+  if (p.na < 2 || p.nb < 1) { ctx->set_error("conv_tc_run: shared-memory plan failed for " + L.name); return B2O_ERR_ARG; }
+  const int smem_bytes = p.off_bar + 512 + 1024;
+
   p.s1 = L.s1; p.t1 = L.t1; p.s2 = L.s2; p.t2 = L.t2; p.relu = L.relu;
-  p.out = out.ptr; p.out_ld = out.ld; p.out_f32 = out_f32;
+  p.out = out.ptr; p.out_ld = out.ld; p.out_f32 = out_f32; p.write_full = write_full;
+  if (want_pool) {
+    if (out_f32 || pool_out->c != L.cout || pool_out->h != in.h / 2 || pool_out->w != in.w / 2 || (pool_out->ld % 8)) {
+      ctx->set_error("conv_tc_run: bad pool view for " + L.name);
+      return B2O_ERR_ARG;
+    }
+    p.pool_out = pool_out->ptr; p.pool_ld = pool_out->ld; p.PH = pool_out->h; p.PW = pool_out->w;
+  }
 
   CUtensorMap amap;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(in.c), static_cast<cuuint64_t>(in.w), static_cast<cuuint64_t>(in.h),
                         static_cast<cuuint64_t>(in.n)};
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.ld) * 2, static_cast<cuuint64_t>(in.ld) * 2 * in.w,
                            static_cast<cuuint64_t>(in.ld) * 2 * in.w * in.h};
-  cuuint32_t box[4] = {BLOCK_K, 1u << p.bw_log2, 1u << p.bh_log2, 1u << p.bn_log2};
+  cuuint32_t box[4] = {static_cast<cuuint32_t>(kch), 1u << p.bw_log2, 1u << p.bh_log2, 1u << p.bn_log2};
+  if (p.halo) { box[1] = 8; box[2] = 18; box[3] = 1; }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in.ptr, dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kch), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     ctx->set_error("cuTensorMapEncodeTiled(activation for " + L.name + ") failed: " +
                    std::to_string(static_cast<int>(r)));
     return B2O_ERR_CUDA;
   }
-  switch (L.block_n) {
-    case 16: return launch<16>(ctx, amap, L, p, st);
-    case 32: return launch<32>(ctx, amap, L, p, st);
-    case 64: return launch<64>(ctx, amap, L, p, st);
-    case 128: return launch<128>(ctx, amap, L, p, st);
-    case 256: return launch<256>(ctx, amap, L, p, st);
-  }
-  ctx->set_error("conv_tc_run: bad block_n");
+#define B2O_TC_CASE(BN, KC) \
+  if (bn == BN && kch == KC) return launch<BN, KC>(ctx, amap, L, p, smem_bytes, st)
+  B2O_TC_CASE(16, 64); B2O_TC_CASE(32, 64); B2O_TC_CASE(64, 64); B2O_TC_CASE(128, 64); B2O_TC_CASE(256, 64);
+  B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32);
+  B2O_TC_CASE(32, 16);
+#undef B2O_TC_CASE
+  ctx->set_error("conv_tc_run: no kernel instance for " + L.name);
   return B2O_ERR_ARG;
 }

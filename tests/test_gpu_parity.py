@@ -52,7 +52,15 @@ CONV_CASES = [
     (1, 1, 300, 3584, 128, 1, 1, 1, 0),     # fc_9 as a 1x1 conv over rows
     (1, 8, 8, 1536, 512, 1, 1, 1, 0),       # upconv1.conv.0
     (1, 96, 96, 64, 64, 3, 1, 1, 0),        # many tiles per CTA (persistent loop, both TMEM stages)
+    (2, 40, 48, 32, 32, 3, 1, 1, 0),        # conv_cls.0: 32-channel K chunk (64B swizzle), resident filters
+    (1, 33, 29, 32, 16, 3, 1, 1, 0),        # conv_cls.4, ragged halo tiles
+    (2, 50, 7, 16, 32, 5, 1, 1, 0),         # STN conv_b: 16-channel K chunk (32B swizzle), 5x5
+    (1, 48, 40, 128, 128, 3, 1, 1, 0),      # halo tiles with a streamed (non-resident) filter bank
+    (1, 32, 24, 256, 512, 3, 1, 1, 0),      # halo tiles, two n-tiles of 256
 ]
+
+ENGINES = [_lib.CONV_SIMT, _lib.CONV_TC_GENERIC, _lib.CONV_AUTO]
+ENGINE_IDS = ["simt", "tcgen05_generic", "tcgen05"]
 
 
 def _torch_conv_reference(x, wgt, k, dil, s1, t1, relu, s2, t2):
@@ -67,7 +75,7 @@ def _torch_conv_reference(x, wgt, k, dil, s1, t1, relu, s2, t2):
     return y.permute(0, 2, 3, 1).contiguous()
 
 
-@pytest.mark.parametrize("engine", [_lib.CONV_SIMT, _lib.CONV_AUTO], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("engine", ENGINES, ids=ENGINE_IDS)
 @pytest.mark.parametrize("case", CONV_CASES, ids=[f"n{c[0]}_{c[1]}x{c[2]}_{c[3]}to{c[4]}_k{c[5]}d{c[6]}" for c in CONV_CASES])
 def test_conv_engine_vs_fp32(ctx, cuda_device, case, engine):
     n, h, w, cin, cout, k, dil, relu, aff = case
@@ -197,7 +205,7 @@ def test_get_boxes_overflow_retry(detector):
 
 
 # ------------------------------------------------------------------------------- CRAFT
-@pytest.mark.parametrize("engine", [_lib.CONV_SIMT, _lib.CONV_AUTO], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("engine", ENGINES, ids=ENGINE_IDS)
 def test_craft_forward_vs_reference_golden(detector, golden_dir, engine):
     g = np.load(os.path.join(golden_dir, "craft.npz"))
     detector.ctx.set_conv_engine(engine)
