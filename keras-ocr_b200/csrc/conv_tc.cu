@@ -167,6 +167,11 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 struct TileCoord { int w0, h0, n0, n_tile; };
 __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
@@ -180,7 +185,8 @@ __device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
 }
 
 // ------------------------------------------------------------------------------------------ kernel
-template <int BLOCK_N, int KCH>
+// MODE: 0 = generic tiles, 1 = halo tiles (3x3, dilation 1), 2 = halo tiles + resident filter bank
+template <int BLOCK_N, int KCH, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                const TcParams p) {
@@ -230,18 +236,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
+  // Every launch requests > 114 KB of shared memory, so this CTA owns the SM and its TMEM allocation
+  // starts at column 0.  Using the literal 0 keeps the accumulator address in a uniform register:
+  // a per-thread value would make ptxas wrap every UTCHMMA in an ELECT / R2UR.BROADCAST loop, which
+  // costs ~120 cycles per MMA (measured with scripts/probes/mma_probe.cu).
+  if (*tmem_slot != 0u) {
+    if (threadIdx.x == 0) printf("b2ocr conv_tc: unexpected TMEM base %u\n", *tmem_slot);
+    __trap();
+  }
+  constexpr uint32_t tmem_base = 0u;
 
+  constexpr bool HALO = MODE >= 1, RESIDENT = MODE == 2;
+  constexpr int TAPS_PER_A = HALO ? 3 : 1;                 // dy taps served by one A stage
   const int taps = p.ksize * p.ksize;
   const int kchunks = p.cin / KCH;
   const int half_k = p.ksize >> 1;
-  const int n_a = (p.halo ? 3 : taps) * kchunks;           // A stages per tile
-  const int taps_per_a = p.halo ? 3 : 1;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      if (p.resident) {                                    // whole filter bank, once per CTA
+      if (RESIDENT) {                                      // whole filter bank, once per CTA
         mbar_expect_tx(res_full, static_cast<uint32_t>(taps * kchunks * B_BYTES));
         for (int tap = 0; tap < taps; ++tap)
           for (int kc = 0; kc < kchunks; ++kc)
@@ -249,79 +263,91 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
+      const int groups = HALO ? 3 : taps;                  // dx positions (halo) or filter taps (generic)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord tc = tile_coord(p, tile);
-        for (int it = 0; it < n_a; ++it) {
-          const int g = it / kchunks, kc = it - g * kchunks;   // g = dx index (halo) or tap (generic)
-          int ax, ay;
-          if (p.halo) { ax = tc.w0 + g - 1; ay = tc.h0 - 1; }
-          else { ax = tc.w0 + (g % p.ksize - half_k) * p.dil; ay = tc.h0 + (g / p.ksize - half_k) * p.dil; }
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(p.a_bytes));
-          tma_load_4d(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tc.n0);
-          if (++sa == p.na) { sa = 0; pa ^= 1; }
-          if (!p.resident) {
-            for (int t = 0; t < taps_per_a; ++t) {
-              const int tap = p.halo ? (t * 3 + g) : g;
-              mbar_wait(&b_empty[sb], pb ^ 1);
-              mbar_expect_tx(&b_full[sb], B_BYTES);
-              tma_load_2d(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, tc.n_tile * BLOCK_N);
-              if (++sb == p.nb) { sb = 0; pb ^= 1; }
+        int ky = 0, kx = 0;
+        for (int g = 0; g < groups; ++g) {
+          const int ax = HALO ? (tc.w0 + g - 1) : (tc.w0 + (kx - half_k) * p.dil);
+          const int ay = HALO ? (tc.h0 - 1) : (tc.h0 + (ky - half_k) * p.dil);
+          for (int kc = 0; kc < kchunks; ++kc) {
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(p.a_bytes));
+            tma_load_4d(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tc.n0);
+            if (++sa == p.na) { sa = 0; pa ^= 1; }
+            if (!RESIDENT) {
+#pragma unroll
+              for (int t = 0; t < TAPS_PER_A; ++t) {
+                const int tap = HALO ? (t * 3 + g) : g;
+                mbar_wait(&b_empty[sb], pb ^ 1);
+                mbar_expect_tx(&b_full[sb], B_BYTES);
+                tma_load_2d(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, tc.n_tile * BLOCK_N);
+                if (++sb == p.nb) { sb = 0; pb ^= 1; }
+              }
             }
           }
+          if (++kx == p.ksize) { kx = 0; ++ky; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=f16, both K-major, N=BLOCK_N, M=128
-      constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
-                                 (static_cast<uint32_t>(BLOCK_M >> 4) << 24);
-      if (p.resident) { mbar_wait(res_full, 0); tcgen05_after_sync(); }
-      int sa = 0, sb = 0, acc = 0;
-      uint32_t pa = 0, pb = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tcgen05_after_sync();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-        uint32_t accumulate = 0;
-        for (int it = 0; it < n_a; ++it) {
-          const int g = it / kchunks, kc = it - g * kchunks;
+    // The whole warp runs the (uniform) control flow so that descriptors, stage indices and the TMEM
+    // address stay in uniform registers; only the tcgen05 instructions are predicated on one elected
+    // lane.  (A single-lane divergent loop costs ~170 cycles of scalar overhead per MMA.)
+    constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
+                               (static_cast<uint32_t>(BLOCK_M >> 4) << 24);   // D=f32, A=B=f16 K-major, N, M=128
+    constexpr uint32_t TAP_DESC = TAP_SHIFT >> 4, B_DESC = B_BYTES >> 4;       // in 16-byte descriptor units
+    const uint64_t a_desc0 = umma_desc<KCH>(smem_u32(smem_a));
+    const uint64_t b_desc0 = umma_desc<KCH>(smem_u32(smem_b));
+    const uint32_t a_step = static_cast<uint32_t>(p.a_stride) >> 4;
+    if (RESIDENT) { mbar_wait(res_full, 0); tcgen05_after_sync(); }
+    int sa = 0, sb = 0, acc = 0;
+    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    const int groups = HALO ? 3 : taps;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      tcgen05_after_sync();
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+      uint32_t accumulate = 0;
+      for (int g = 0; g < groups; ++g) {
+        for (int kc = 0; kc < kchunks; ++kc) {
           mbar_wait(&a_full[sa], pa);
           tcgen05_after_sync();
-          const uint32_t a_base = smem_u32(smem_a + sa * p.a_stride);
-          for (int t = 0; t < taps_per_a; ++t) {
-            uint32_t b_addr;
-            if (p.resident) {
-              const int tap = p.halo ? (t * 3 + g) : g;
-              b_addr = smem_u32(smem_b + (tap * kchunks + kc) * B_BYTES);
+          const uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa) * a_step);
+#pragma unroll
+          for (int t = 0; t < TAPS_PER_A; ++t) {
+            uint64_t bdesc;
+            if (RESIDENT) {
+              bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>((t * 3 + g) * kchunks + kc) * B_DESC);
             } else {
               mbar_wait(&b_full[sb], pb);
               tcgen05_after_sync();
-              b_addr = smem_u32(smem_b + sb * B_BYTES);
+              bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sb) * B_DESC);
             }
-            // dy tap t of a halo stage = the same stage shifted by t rows of 8 pixels
-            const uint64_t adesc = umma_desc<KCH>(a_base + static_cast<uint32_t>(t * TAP_SHIFT));
-            const uint64_t bdesc = umma_desc<KCH>(b_addr);
+            if (elect_one()) {
 #pragma unroll
-            for (int k = 0; k < KSTEPS; ++k) {
-              // advance 16 fp16 = 32 B along K inside the swizzle atom: +2 in 16-byte units
-              umma_f16(d_tmem, adesc + static_cast<uint64_t>(2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
-                       accumulate);
-              accumulate = 1;
+              for (int k = 0; k < KSTEPS; ++k)
+                // dy tap t = the stage shifted by t rows of 8 pixels; k-step = +32 B inside the swizzle atom
+                umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                         idesc, (k == 0) ? accumulate : 1u);
             }
-            if (!p.resident) {
-              umma_commit(&b_empty[sb]);
+            __syncwarp();
+            accumulate = 1;
+            if (!RESIDENT) {
+              if (elect_one()) umma_commit(&b_empty[sb]);
+              __syncwarp();
               if (++sb == p.nb) { sb = 0; pb ^= 1; }
             }
           }
-          umma_commit(&a_empty[sa]);                      // frees the A slot when its MMAs retire
+          if (elect_one()) umma_commit(&a_empty[sa]);      // frees the A slot when its MMAs retire
+          __syncwarp();
           if (++sa == p.na) { sa = 0; pa ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
     // ===================================================================== epilogue (warps 2..5)
@@ -473,12 +499,12 @@ double pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
   return best_cover;
 }
 
-template <int BLOCK_N, int KCH>
+template <int BLOCK_N, int KCH, int MODE>
 int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, int smem_bytes,
            cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              232448));
     configured = true;
   }
@@ -489,7 +515,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     B2O_CUDA_CHECK(ctx, cudaEventCreate(&e1));
     B2O_CUDA_CHECK(ctx, cudaEventRecord(e0, st));
   }
-  conv_tc_kernel<BLOCK_N, KCH><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
+  conv_tc_kernel<BLOCK_N, KCH, MODE><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
   B2O_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
     B2O_CUDA_CHECK(ctx, cudaEventRecord(e1, st));
@@ -594,7 +620,8 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
     p.off_bar = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
   }
   if (p.na < 2 || p.nb < 1) { ctx->set_error("conv_tc_run: shared-memory plan failed for " + L.name); return B2O_ERR_ARG; }
-  const int smem_bytes = p.off_bar + 512 + 1024;
+  int smem_bytes = p.off_bar + 512 + 1024;
+  if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;    // one CTA per SM (TMEM base 0, see kernel)
 
   p.s1 = L.s1; p.t1 = L.t1; p.s2 = L.s2; p.t2 = L.t2; p.relu = L.relu;
   p.out = out.ptr; p.out_ld = out.ld; p.out_f32 = out_f32; p.write_full = write_full;
@@ -622,8 +649,12 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
                    std::to_string(static_cast<int>(r)));
     return B2O_ERR_CUDA;
   }
-#define B2O_TC_CASE(BN, KC) \
-  if (bn == BN && kch == KC) return launch<BN, KC>(ctx, amap, L, p, smem_bytes, st)
+#define B2O_TC_CASE(BN, KC)                                                            \
+  if (bn == BN && kch == KC) {                                                         \
+    if (p.resident) return launch<BN, KC, 2>(ctx, amap, L, p, smem_bytes, st);         \
+    if (p.halo) return launch<BN, KC, 1>(ctx, amap, L, p, smem_bytes, st);             \
+    return launch<BN, KC, 0>(ctx, amap, L, p, smem_bytes, st);                         \
+  }
   B2O_TC_CASE(16, 64); B2O_TC_CASE(32, 64); B2O_TC_CASE(64, 64); B2O_TC_CASE(128, 64); B2O_TC_CASE(256, 64);
   B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32);
   B2O_TC_CASE(32, 16);
