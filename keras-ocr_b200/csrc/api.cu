@@ -110,7 +110,7 @@ struct CraftPlan {
   int n, h1, w1, h2, w2, h4, w4, h8, w8, h16, w16;
   size_t off_a, off_b, off_p1, off_c, off_cat4, off_p2, off_d, off_cat3, off_e, off_p3, off_f, off_cat2, off_g, off_p4,
       off_hh, off_cat1, off_mp, off_s5a, off_u1a, off_u1b, off_u2a, off_u2b, off_u3a, off_u3b, off_u4a, off_u4b, off_h1,
-      off_h2, off_h3, bytes;
+      off_h2, off_h3, off_x16, bytes;
 };
 
 CraftPlan plan_craft(int n, int h, int w) {
@@ -134,6 +134,7 @@ CraftPlan plan_craft(int n, int h, int w) {
   p.off_u2b = take(p.h8, p.w8, 128); p.off_u3a = take(p.h4, p.w4, 128); p.off_u3b = take(p.h4, p.w4, 64);
   p.off_u4a = take(p.h2, p.w2, 64); p.off_u4b = take(p.h2, p.w2, 32); p.off_h1 = take(p.h2, p.w2, 32);
   p.off_h2 = take(p.h2, p.w2, 32); p.off_h3 = take(p.h2, p.w2, 16);
+  p.off_x16 = take(p.h1, p.w1, 16);       // normalised input, 3 -> 16 channels, for the tensor-core stem
   p.bytes = off;
   return p;
 }
@@ -259,6 +260,13 @@ extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
     auto wget = [wd, cin, k](int o, int c, int ky, int kx) { return wd[((static_cast<size_t>(o) * cin + c) * k + ky) * k + kx]; };
     ConvLayer& L = ctx->craft[s.name];
     B2O_RETURN_IF(build_layer(ctx, L, s.name, s.cin, s.cout, s.k, s.dil, s.relu, wget, s1, t1, nullptr, nullptr, s.cin == 3));
+    if (s.cin == 3) {      // tensor-core stem: same filters over a 16-channel (zero-padded) input
+      auto wget16 = [wd, cin, k](int o, int c, int ky, int kx) {
+        return c < 3 ? wd[((static_cast<size_t>(o) * cin + c) * k + ky) * k + kx] : 0.0f;
+      };
+      ConvLayer& L16 = ctx->craft["stem16"];
+      B2O_RETURN_IF(build_layer(ctx, L16, "stem16", 16, s.cout, s.k, 1, s.relu, wget16, s1, t1, nullptr, nullptr, false));
+    }
   }
   ctx->craft_loaded = true;
   return B2O_OK;
@@ -404,7 +412,13 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
   const TensorView h1 = V(p.off_h1, p.h2, p.w2, 32), h2 = V(p.off_h2, p.h2, p.w2, 32), h3 = V(p.off_h3, p.h2, p.w2, 16);
 
   // encoder (detection.py:312-324); taps s1..s4 are written straight into the concat buffers
-  B2O_RETURN_IF(stem_rgb_run(ctx, L("basenet.slice1.0"), img, n, h, w, a, st));
+  if (ctx->conv_engine == B2O_CONV_SIMT || L("stem16").block_n == 0) {
+    B2O_RETURN_IF(stem_rgb_run(ctx, L("basenet.slice1.0"), img, n, h, w, a, st));          // fp32 CUDA-core stem
+  } else {
+    const TensorView x16 = V(p.off_x16, p.h1, p.w1, 16);
+    B2O_RETURN_IF(normalize16_run(ctx, img, n, h, w, x16.ptr, st));
+    B2O_RETURN_IF(conv_run(ctx, L("stem16"), x16, a, 0, st));
+  }
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.3"), a, b, 0, st, &p1, 0));     // conv + fused 2x2 max pool
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.7"), p1, c, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.10"), c, s1, 0, st, &p2, 1));   // tap s1 (full) + pooled

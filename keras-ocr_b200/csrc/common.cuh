@@ -92,6 +92,7 @@ int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Tenso
              int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1);
 int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, int h, int w,
                  const TensorView& out, cudaStream_t st);
+int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st);
 int stem_crnn_run(b2o_ctx* ctx, const ConvLayer& L, const __half* x, int b, const TensorView& out,
                   cudaStream_t st);
 int maxpool2_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cudaStream_t st);

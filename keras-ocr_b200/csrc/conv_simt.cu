@@ -149,6 +149,30 @@ stem_rgb_kernel(const uint8_t* __restrict__ img, int N, int H, int W, const floa
   }
 }
 
+// compute_input (detection.py:34-42) into a 16-channel fp16 image (r, g, b, 0 x 13): the A operand of
+// the tensor-core stem convolution (3x3, 16 -> 64 with the 13 padding channels weighted 0).
+__global__ void normalize16_kernel(const uint8_t* __restrict__ img, long long total, __half* __restrict__ out) {
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const double mean[3] = {0.485 * 255, 0.456 * 255, 0.406 * 255};
+  const double stdv[3] = {0.229 * 255, 0.224 * 255, 0.225 * 255};
+  const uint8_t* ip = img + p * 3;
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float t = static_cast<float>(static_cast<double>(ip[c]) - mean[c]);
+    v[c] = static_cast<float>(static_cast<double>(t) / stdv[c]);
+  }
+  const __half2 rg = __floats2half2_rn(v[0], v[1]), b0 = __floats2half2_rn(v[2], 0.0f);
+  uint4 lo, hi = make_uint4(0u, 0u, 0u, 0u);
+  lo.x = *reinterpret_cast<const uint32_t*>(&rg);
+  lo.y = *reinterpret_cast<const uint32_t*>(&b0);
+  lo.z = 0u; lo.w = 0u;
+  uint4* o = reinterpret_cast<uint4*>(out + p * 16);
+  o[0] = lo;
+  o[1] = hi;
+}
+
 // CRNN conv_1: x (B,200,31) fp16 -> (B,200,31,64) fp16, 3x3 same, bias + ReLU.
 __global__ void __launch_bounds__(128)
 stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt /*[9][64]*/,
@@ -368,6 +392,13 @@ int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, in
                  cudaStream_t st) {
   const long long total = static_cast<long long>(n) * h * w;
   stem_rgb_kernel<<<blocks_for(total, 128), 128, 0, st>>>(img, n, h, w, L.w_f32, L.s1, L.t1, out.ptr, out.ld);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(n) * h * w;
+  normalize16_kernel<<<blocks_for(total, 256), 256, 0, st>>>(img, total, out);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

@@ -18,7 +18,7 @@
 // * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16); fp32
 //   accumulators live in TMEM (2 stages): the epilogue of tile i overlaps the main loop of tile i+1.
 // * warp roles: warp0 = TMA producer (A ring + B ring), warp1 = TMEM allocator + MMA issuer,
-//   warps 2..5 = epilogue: tcgen05.ld -> scale/shift/ReLU/affine -> fp16|fp32 NHWC stores (possibly
+//   warps 2..9 = epilogue: tcgen05.ld -> scale/shift/ReLU/affine -> fp16|fp32 NHWC stores (possibly
 //   into a channel slice of a concat buffer) and, optionally, the fused 2x2 max-pool output.
 // * persistent: grid = min(#tiles, #SMs); n-tiles of one pixel tile run back to back.
 #include <string.h>
@@ -29,7 +29,8 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 per TMEM quadrant)
+constexpr int EPI_THREADS = 256;
 constexpr int SMEM_TOTAL = 230 * 1024;     // dynamic shared memory we allow ourselves (max 227 KB = 232448 B)
 constexpr int MAX_RING = 8;
 
@@ -173,16 +174,30 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-struct TileCoord { int w0, h0, n0, n_tile; };
-__device__ __forceinline__ TileCoord tile_coord(const TcParams& p, int tile) {
-  TileCoord t;
-  t.n_tile = tile % p.n_tiles;
-  const int m_tile = tile / p.n_tiles;
-  t.w0 = (m_tile % p.tiles_w) << p.bw_log2;
-  t.h0 = ((m_tile / p.tiles_w) % p.tiles_h) << p.bh_log2;
-  t.n0 = (m_tile / (p.tiles_w * p.tiles_h)) << p.bn_log2;
-  return t;
-}
+// Walks this CTA's tiles (blockIdx.x, +gridDim.x, ...) keeping the mixed-radix coordinate
+// (n_tile, tile_w, tile_h, tile_n) incrementally: no integer divisions in the per-tile path.
+struct TileIter {
+  int c0, c1, c2, c3;        // n_tile, tile_w, tile_h, tile_n
+  int d0, d1, d2, d3;        // gridDim.x in the same radix
+  int r0, r1, r2;            // radices: n_tiles, tiles_w, tiles_h
+  int tile, step, total;
+  __device__ __forceinline__ TileIter(const TcParams& p) {
+    r0 = p.n_tiles; r1 = p.tiles_w; r2 = p.tiles_h;
+    total = p.total_tiles; step = static_cast<int>(gridDim.x); tile = static_cast<int>(blockIdx.x);
+    int t = tile;
+    c0 = t % r0; t /= r0; c1 = t % r1; t /= r1; c2 = t % r2; c3 = t / r2;
+    t = step;
+    d0 = t % r0; t /= r0; d1 = t % r1; t /= r1; d2 = t % r2; d3 = t / r2;
+  }
+  __device__ __forceinline__ bool valid() const { return tile < total; }
+  __device__ __forceinline__ void next() {
+    tile += step;
+    c0 += d0; if (c0 >= r0) { c0 -= r0; ++c1; }
+    c1 += d1; if (c1 >= r1) { c1 -= r1; ++c2; }
+    c2 += d2; if (c2 >= r2) { c2 -= r2; ++c3; }
+    c3 += d3;
+  }
+};
 
 // ------------------------------------------------------------------------------------------ kernel
 // MODE: 0 = generic tiles, 1 = halo tiles (3x3, dilation 1), 2 = halo tiles + resident filter bank
@@ -222,7 +237,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], 128);
+      mbar_init(&tmem_empty[s], EPI_THREADS);
     }
     mbar_init(res_full, 1);
     fence_barrier_init();
@@ -264,16 +279,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const int groups = HALO ? 3 : taps;                  // dx positions (halo) or filter taps (generic)
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(p, tile);
+      for (TileIter ti(p); ti.valid(); ti.next()) {
+        const int tw0 = ti.c1 << p.bw_log2, th0 = ti.c2 << p.bh_log2, tn0 = ti.c3 << p.bn_log2, t_ntile = ti.c0;
         int ky = 0, kx = 0;
         for (int g = 0; g < groups; ++g) {
-          const int ax = HALO ? (tc.w0 + g - 1) : (tc.w0 + (kx - half_k) * p.dil);
-          const int ay = HALO ? (tc.h0 - 1) : (tc.h0 + (ky - half_k) * p.dil);
+          const int ax = HALO ? (tw0 + g - 1) : (tw0 + (kx - half_k) * p.dil);
+          const int ay = HALO ? (th0 - 1) : (th0 + (ky - half_k) * p.dil);
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&a_empty[sa], pa ^ 1);
             mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(p.a_bytes));
-            tma_load_4d(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tc.n0);
+            tma_load_4d(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tn0);
             if (++sa == p.na) { sa = 0; pa ^= 1; }
             if (!RESIDENT) {
 #pragma unroll
@@ -281,7 +296,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                 const int tap = HALO ? (t * 3 + g) : g;
                 mbar_wait(&b_empty[sb], pb ^ 1);
                 mbar_expect_tx(&b_full[sb], B_BYTES);
-                tma_load_2d(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, tc.n_tile * BLOCK_N);
+                tma_load_2d(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, t_ntile * BLOCK_N);
                 if (++sb == p.nb) { sb = 0; pb ^= 1; }
               }
             }
@@ -350,8 +365,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 2..9)
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may touch
+    const int half = (warp - 2) >> 2;                     // the two warps of a quadrant split the column chunks
     const int row = quad * 32 + lane;                     // accumulator row = pixel inside the tile
     const int bw_mask = (1 << p.bw_log2) - 1, bh_mask = (1 << p.bh_log2) - 1;
     const int wi = row & bw_mask;
@@ -359,12 +375,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     const int ni = row >> (p.bw_log2 + p.bh_log2);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(p, tile);
-      const int w = tc.w0 + wi, h = tc.h0 + hi, n = tc.n0 + ni;
+    for (TileIter ti(p); ti.valid(); ti.next()) {
+      const int w = (ti.c1 << p.bw_log2) + wi, h = (ti.c2 << p.bh_log2) + hi, n = (ti.c3 << p.bn_log2) + ni;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
-      const int c_base = tc.n_tile * BLOCK_N;
+      const int c_base = ti.c0 * BLOCK_N;
       // fused 2x2/2 max pool (halo tiles: lane^1 = w neighbour, lane^8 = h neighbour)
       const bool pool_writer = p.pool_out != nullptr && !(w & 1) && !(h & 1) && (w >> 1) < p.PW && (h >> 1) < p.PH &&
                                n < p.N;
@@ -374,7 +389,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 #pragma unroll 1
-      for (int ch = 0; ch < BLOCK_N / CH; ++ch) {
+      for (int ch = half; ch < BLOCK_N / CH; ch += 2) {
         uint32_t v[CH];
         tmem_ld<CH>(taddr + static_cast<uint32_t>(ch * CH), v);
         tmem_ld_wait();
@@ -537,7 +552,7 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
   while (bn > 16 && (L.cout % bn != 0)) bn >>= 1;
   if (L.cout % bn != 0) return B2O_OK;
   if (L.kch == 32 && bn > 32) return B2O_OK;               // instantiated combinations only
-  if (L.kch == 16 && bn != 32) return B2O_OK;
+  if (L.kch == 16 && bn != 32 && bn != 64) return B2O_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return B2O_ERR_CUDA; }
   const cuuint64_t ktot = static_cast<cuuint64_t>(L.ksize) * L.ksize * L.cin;
@@ -657,7 +672,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   }
   B2O_TC_CASE(16, 64); B2O_TC_CASE(32, 64); B2O_TC_CASE(64, 64); B2O_TC_CASE(128, 64); B2O_TC_CASE(256, 64);
   B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32);
-  B2O_TC_CASE(32, 16);
+  B2O_TC_CASE(32, 16); B2O_TC_CASE(64, 16);
 #undef B2O_TC_CASE
   ctx->set_error("conv_tc_run: no kernel instance for " + L.name);
   return B2O_ERR_ARG;

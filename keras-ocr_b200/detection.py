@@ -66,6 +66,8 @@ class Detector:
         self.ctx = _lib.Context(self.device_index)
         self.ctx.load_craft(tensors)
         self.max_boxes = 256
+        self._ws = None                  # reusable CRAFT workspace (grown on demand)
+        self._box_ws = None
 
     # ------------------------------------------------------------------ device-resident API
     def predict_device(self, images_t):
@@ -75,7 +77,10 @@ class Detector:
         scores = torch.empty((n, h // 2, w // 2, 2), dtype=torch.float32, device=self.device)
         nbytes = self.ctx.craft_workspace_bytes(n, h, w)
         assert nbytes > 0, "image too small for CRAFT (needs H, W >= 32)"
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        ws = self._ws
         self.ctx.craft_forward(images_t.data_ptr(), n, h, w, scores.data_ptr(), ws.data_ptr(), nbytes, stream)
         return scores
 
@@ -90,7 +95,10 @@ class Detector:
             boxes = torch.empty((n, m, 4, 2), dtype=torch.float32, device=self.device)
             counts = torch.empty((n,), dtype=torch.int32, device=self.device)
             nbytes = self.ctx.boxes_workspace_bytes(n, hs, ws_, m)
-            wsp = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            if self._box_ws is None or self._box_ws.numel() < nbytes:
+                self._box_ws = None
+                self._box_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+            wsp = self._box_ws
             self.ctx.get_boxes(scores.data_ptr(), n, hs, ws_, float(detection_threshold), float(text_threshold),
                                float(link_threshold), int(size_threshold), boxes.data_ptr(), counts.data_ptr(), m,
                                wsp.data_ptr(), nbytes, stream)

@@ -12,8 +12,19 @@ TARGET_HEIGHT, TARGET_WIDTH, STEPS = 31, 200, 48                # DEFAULT_BUILD_
 
 
 def labels_to_text(rows, alphabet=DEFAULT_ALPHABET):
-    """reference recognition.py:527-534."""
+    """reference recognition.py:527-534: drop blank / -1, map indices to characters.
+
+    The CTC decoder emits the kept labels as a prefix of each row, so the common case is a table
+    lookup plus a NUL-terminated view (no per-character Python loop); any other row layout falls
+    back to the reference's element-wise filter."""
     blank = len(alphabet)
+    rows = np.asarray(rows)
+    if rows.ndim == 2 and rows.size and alphabet.isascii():
+        keep = (rows != blank) & (rows != -1)
+        if bool(np.all(keep[:, :-1] >= keep[:, 1:])) and bool(np.all(rows[keep] >= 0)) and bool(np.all(rows[keep] < blank)):
+            lut = np.frombuffer((alphabet + "\0").encode("ascii"), dtype=np.uint8)
+            codes = np.ascontiguousarray(lut[np.where(keep, rows, blank)])
+            return [b.decode("ascii") for b in codes.view(f"S{rows.shape[1]}").ravel().tolist()]
     return ["".join(alphabet[idx] for idx in row if idx not in (blank, -1)) for row in rows]
 
 
@@ -51,6 +62,7 @@ class Recognizer:
         self.ctx.load_crnn(tensors)
         self.keep_workspace = False      # tests set this to read intermediate taps
         self._last_ws = None
+        self._ws = None                  # reusable CRNN workspace (grown on demand)
 
     # ------------------------------------------------------------------ device-resident API
     def gray_device(self, images_t):
@@ -75,7 +87,10 @@ class Recognizer:
         b = crnn_in.shape[0]
         labels = torch.empty((b, STEPS), dtype=torch.int32, device=self.device)
         nbytes = self.ctx.crnn_workspace_bytes(b)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        if self._ws is None or self._ws.numel() < nbytes:
+            self._ws = None
+            self._ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        ws = self._ws
         self.ctx.crnn_forward(crnn_in.data_ptr(), b, labels.data_ptr(), ws.data_ptr(), nbytes,
                               torch.cuda.current_stream(self.device).cuda_stream)
         self._last_ws = (ws, b) if self.keep_workspace else None

@@ -57,6 +57,7 @@ CONV_CASES = [
     (2, 50, 7, 16, 32, 5, 1, 1, 0),         # STN conv_b: 16-channel K chunk (32B swizzle), 5x5
     (1, 48, 40, 128, 128, 3, 1, 1, 0),      # halo tiles with a streamed (non-resident) filter bank
     (1, 32, 24, 256, 512, 3, 1, 1, 0),      # halo tiles, two n-tiles of 256
+    (2, 40, 56, 16, 64, 3, 1, 1, 0),        # tensor-core stem shape: 16-channel chunk, resident filters
 ]
 
 ENGINES = [_lib.CONV_SIMT, _lib.CONV_TC_GENERIC, _lib.CONV_AUTO]
