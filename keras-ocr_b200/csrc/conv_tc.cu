@@ -18,19 +18,23 @@
 // * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16); fp32
 //   accumulators live in TMEM (2 stages): the epilogue of tile i overlaps the main loop of tile i+1.
 // * warp roles: warp0 = TMA producer (A ring + B ring), warp1 = TMEM allocator + MMA issuer,
-//   warps 2..9 = epilogue: tcgen05.ld -> scale/shift/ReLU/affine -> fp16|fp32 NHWC stores (possibly
+//   warps 3..18 = epilogue: tcgen05.ld -> scale/shift/ReLU/affine -> fp16|fp32 NHWC stores (possibly
 //   into a channel slice of a concat buffer) and, optionally, the fused 2x2 max-pool output.
 // * persistent: grid = min(#tiles, #SMs); n-tiles of one pixel tile run back to back.
 #include <string.h>
 
 #include "common.cuh"
 
+// Development counters of the MMA warp (cycles): [cta][0]=total, [1]=wait tmem_empty, [2]=wait a_full,
+// [3]=wait b_full, [4]=tiles.  Read back with b2o_debug_read_tc().
+__device__ unsigned long long g_tc_debug[160 * 8];
+
 namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 320;          // warp0 TMA, warp1 MMA, warps 2..9 epilogue (2 per TMEM quadrant)
-constexpr int EPI_THREADS = 256;
+constexpr int NUM_THREADS = 608;          // warp0 TMA, warps 1-2 MMA issuers, warps 3..18 epilogue (4 per TMEM quadrant)
+constexpr int EPI_THREADS = 512;
 constexpr int SMEM_TOTAL = 230 * 1024;     // dynamic shared memory we allow ourselves (max 227 KB = 232448 B)
 constexpr int MAX_RING = 8;
 
@@ -208,8 +212,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   constexpr int B_BYTES = BLOCK_N * KCH * 2;
   constexpr int TAP_SHIFT = 16 * KCH;                      // bytes of one 8-pixel row group (= SBO)
   constexpr int KSTEPS = KCH / UMMA_K;
-  constexpr int TMEM_COLS = (2 * BLOCK_N) < 32 ? 32 : (2 * BLOCK_N);
-  constexpr int CH = BLOCK_N >= 32 ? 32 : 16;              // accumulator columns per tcgen05.ld
+  // TMEM accumulator stages: as many as fit in the 512 columns (max 8).  With only two, a short-K tile is
+  // bound by the *latency* of the epilogue hand-off (tmem_full -> LDTM -> stores -> tmem_empty), not by its
+  // throughput; with 4-8 the MMA warp runs several tiles ahead of the epilogue warps.
+  constexpr int ACC_STAGES = (512 / BLOCK_N) > 8 ? 8 : (512 / BLOCK_N);
+  constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N) < 32 ? 32 : (ACC_STAGES * BLOCK_N);
+  constexpr int CH = 16;                                   // accumulator columns per tcgen05.ld (per epilogue warp visit)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -219,8 +227,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   uint64_t* b_full = a_empty + MAX_RING;
   uint64_t* b_empty = b_full + MAX_RING;
   uint64_t* tmem_full = b_empty + MAX_RING;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;
+  uint64_t* tmem_empty = tmem_full + MAX_RING;
+  uint64_t* order_bar = tmem_empty + MAX_RING;
+  uint64_t* res_full = order_bar + MAX_RING;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 1);
 
   const int warp = threadIdx.x >> 5;
@@ -235,9 +244,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       mbar_init(&b_full[s], 1);
       mbar_init(&b_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&tmem_full[s], 1);
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&tmem_full[s], 2);                       // one arrival per issuing warp
       mbar_init(&tmem_empty[s], EPI_THREADS);
+      mbar_init(&order_bar[s], 1);
     }
     mbar_init(res_full, 1);
     fence_barrier_init();
@@ -305,69 +315,115 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    // The whole warp runs the (uniform) control flow so that descriptors, stage indices and the TMEM
-    // address stay in uniform registers; only the tcgen05 instructions are predicated on one elected
-    // lane.  (A single-lane divergent loop costs ~170 cycles of scalar overhead per MMA.)
+  } else if (warp == 1 || warp == 2) {
+    // ===================================================================== MMA issuers (two warps)
+    // The tensor pipe accepts MMAs with (almost) no queue, so the ~80-100 cycles of scalar work an
+    // issuing warp spends per A stage (barrier wait, fences, descriptor arithmetic, commits) would
+    // leave it idle -- ruinous for small-N layers whose MMAs take only 48-64 cycles.  Two warps
+    // therefore take alternate A stages: one prepares while the other's MMAs execute.  Each warp
+    // runs warp-converged (uniform-register operands; only the tcgen05 instructions are predicated
+    // on one elected lane) and commits only the stages it issued (tcgen05.commit tracks the MMAs of
+    // the executing thread).  The accumulator-zeroing MMA of a tile belongs to the owner of the
+    // tile's first stage; the other warp waits on order_bar until it has been issued.
     constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                (static_cast<uint32_t>(BLOCK_M >> 4) << 24);   // D=f32, A=B=f16 K-major, N, M=128
     constexpr uint32_t TAP_DESC = TAP_SHIFT >> 4, B_DESC = B_BYTES >> 4;       // in 16-byte descriptor units
+    const int me = warp - 1;
     const uint64_t a_desc0 = umma_desc<KCH>(smem_u32(smem_a));
     const uint64_t b_desc0 = umma_desc<KCH>(smem_u32(smem_b));
     const uint32_t a_step = static_cast<uint32_t>(p.a_stride) >> 4;
     if (RESIDENT) { mbar_wait(res_full, 0); tcgen05_after_sync(); }
     int sa = 0, sb = 0, acc = 0;
-    uint32_t pa = 0, pb = 0, acc_phase = 0;
+    uint32_t pa = 0, pb = 0, acc_phase = 0, q = 0;          // q = global A-stage counter (ownership parity)
     const int groups = HALO ? 3 : taps;
+    long long dbg_t = 0, dbg_a = 0, dbg_b = 0, dbg_tiles = 0;
+    const long long dbg_start = clock64();
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      { const long long c0 = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); dbg_t += clock64() - c0; ++dbg_tiles; }
       tcgen05_after_sync();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-      uint32_t accumulate = 0;
+      const bool zero_owner = (static_cast<int>(q & 1u) == me);
+      bool need_order = !zero_owner, first = true, issued = false;
       for (int g = 0; g < groups; ++g) {
         for (int kc = 0; kc < kchunks; ++kc) {
-          mbar_wait(&a_full[sa], pa);
-          tcgen05_after_sync();
-          const uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa) * a_step);
+          if (static_cast<int>(q & 1u) == me) {
+            { const long long c0 = clock64(); mbar_wait(&a_full[sa], pa); dbg_a += clock64() - c0; }
+            if (need_order) { mbar_wait(&order_bar[acc], acc_phase); need_order = false; }
+            const uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa) * a_step);
+            const bool zeroing = first && zero_owner;      // this stage holds the tile's accumulator-zeroing MMA
+            if (RESIDENT || TAPS_PER_A == 1) {
+              // ONE elected region per stage: all taps' MMAs back to back, then the commits (every scalar
+              // instruction between two UTCHMMAs is exposed because the pipe has no queue to speak of)
+              uint64_t bdesc[TAPS_PER_A];
 #pragma unroll
-          for (int t = 0; t < TAPS_PER_A; ++t) {
-            uint64_t bdesc;
-            if (RESIDENT) {
-              bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>((t * 3 + g) * kchunks + kc) * B_DESC);
-            } else {
-              mbar_wait(&b_full[sb], pb);
+              for (int t = 0; t < TAPS_PER_A; ++t)
+                bdesc[t] = b_desc0 + static_cast<uint64_t>(
+                               static_cast<uint32_t>(RESIDENT ? ((t * 3 + g) * kchunks + kc) : sb) * B_DESC);
+              if (!RESIDENT) { const long long c0 = clock64(); mbar_wait(&b_full[sb], pb); dbg_b += clock64() - c0; }
               tcgen05_after_sync();
-              bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sb) * B_DESC);
-            }
-            if (elect_one()) {
+              if (elect_one()) {
 #pragma unroll
-              for (int k = 0; k < KSTEPS; ++k)
-                // dy tap t = the stage shifted by t rows of 8 pixels; k-step = +32 B inside the swizzle atom
-                umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k),
-                         idesc, (k == 0) ? accumulate : 1u);
+                for (int t = 0; t < TAPS_PER_A; ++t) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    // dy tap t = the stage shifted by t rows of 8 pixels; k-step = +32 B inside the swizzle atom
+                    umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc[t] + static_cast<uint64_t>(2 * k),
+                             idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
+                }
+                if (!RESIDENT) umma_commit(&b_empty[sb]);
+                umma_commit(&a_empty[sa]);                 // frees the A slot when this warp's MMAs retire
+                if (zeroing) mbar_arrive(&order_bar[acc]); // the zeroing MMA is in the pipe
+              }
+            } else {
+              // halo tiles with a streamed filter bank: one B slot per dy tap, waited for tap by tap
+              int sbl = sb;
+              uint32_t pbl = pb;
+              tcgen05_after_sync();
+#pragma unroll
+              for (int t = 0; t < TAPS_PER_A; ++t) {
+                { const long long c0 = clock64(); mbar_wait(&b_full[sbl], pbl); dbg_b += clock64() - c0; }
+                tcgen05_after_sync();
+                const uint64_t bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sbl) * B_DESC);
+                if (elect_one()) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k)
+                    umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                             idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
+                  umma_commit(&b_empty[sbl]);
+                  if (t == TAPS_PER_A - 1) umma_commit(&a_empty[sa]);
+                  if (t == 0 && zeroing) mbar_arrive(&order_bar[acc]);
+                }
+                __syncwarp();
+                if (++sbl == p.nb) { sbl = 0; pbl ^= 1; }
+              }
             }
             __syncwarp();
-            accumulate = 1;
-            if (!RESIDENT) {
-              if (elect_one()) umma_commit(&b_empty[sb]);
-              __syncwarp();
-              if (++sb == p.nb) { sb = 0; pb ^= 1; }
-            }
+            issued = true;
           }
-          if (elect_one()) umma_commit(&a_empty[sa]);      // frees the A slot when its MMAs retire
-          __syncwarp();
+          first = false;
+          ++q;
           if (++sa == p.na) { sa = 0; pa ^= 1; }
+          if (!RESIDENT) {
+#pragma unroll
+            for (int t = 0; t < TAPS_PER_A; ++t) { if (++sb == p.nb) { sb = 0; pb ^= 1; } }
+          }
         }
       }
-      if (elect_one()) umma_commit(&tmem_full[acc]);
+      if (elect_one()) {
+        if (issued) umma_commit(&tmem_full[acc]); else mbar_arrive(&tmem_full[acc]);
+      }
       __syncwarp();
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0 && blockIdx.x < 160 && me == 0) {
+      unsigned long long* d = g_tc_debug + blockIdx.x * 8;
+      d[0] = static_cast<unsigned long long>(clock64() - dbg_start);
+      d[1] = dbg_t; d[2] = dbg_a; d[3] = dbg_b; d[4] = dbg_tiles;
     }
   } else {
-    // ===================================================================== epilogue (warps 2..9)
+    // ===================================================================== epilogue (warps 3..18)
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may touch
-    const int half = (warp - 2) >> 2;                     // the two warps of a quadrant split the column chunks
+    const int sub = (warp - 3) >> 2;                      // the four warps of a quadrant split the column chunks
     const int row = quad * 32 + lane;                     // accumulator row = pixel inside the tile
     const int bw_mask = (1 << p.bw_log2) - 1, bh_mask = (1 << p.bh_log2) - 1;
     const int wi = row & bw_mask;
@@ -389,7 +445,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 #pragma unroll 1
-      for (int ch = half; ch < BLOCK_N / CH; ch += 2) {
+      for (int ch = sub; ch < BLOCK_N / CH; ch += 4) {
         uint32_t v[CH];
         tmem_ld<CH>(taddr + static_cast<uint32_t>(ch * CH), v);
         tmem_ld_wait();
@@ -461,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       }
       tcgen05_before_sync();
       mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -676,4 +732,10 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
 #undef B2O_TC_CASE
   ctx->set_error("conv_tc_run: no kernel instance for " + L.name);
   return B2O_ERR_ARG;
+}
+
+extern "C" int b2o_debug_read_tc(unsigned long long* out_host, int n) {
+  if (!out_host || n <= 0 || n > 160 * 8) return B2O_ERR_ARG;
+  return cudaMemcpyFromSymbol(out_host, g_tc_debug, static_cast<size_t>(n) * sizeof(unsigned long long)) == cudaSuccess
+             ? B2O_OK : B2O_ERR_CUDA;
 }

@@ -20,13 +20,16 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
                ::"r"(d), "l"(a), "l"(b), "r"(idesc), "r"(acc) : "memory");
 }
 template <int N, int NACC>
-__global__ void __launch_bounds__(128, 1) probe(int n_mma, int same_operands, long long* out) {
+__global__ void __launch_bounds__(256, 1) probe(int n_mma, int same_operands, long long* out, int mode, const uint4* gsrc) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < (128 * 128 + 256 * 128) * 4 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = 0;
+  for (int i = threadIdx.x; i < (128 * 128 + 256 * 128) * 4 / 4; i += blockDim.x) ((uint32_t*)smem)[i] = (mode & 1) ? (0x3c003c00u ^ (i * 2654435761u & 0x03ff03ffu)) : 0;
+  __shared__ uint64_t cbar;
+  __shared__ volatile int stop_flag;
+  if (threadIdx.x == 0) { stop_flag = 0; asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&cbar))); }
   if (threadIdx.x == 0) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -63,6 +66,30 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, int same_operands, lo
     }
     long long t2 = clock64();
     if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    stop_flag = 1;
+  } else if ((mode & 2) && (warp == 2 || warp == 3 || warp == 4 || warp == 5)) {
+    // epilogue-like TMEM readers on the upper columns
+    uint32_t v[16]; float acc = 0.f;
+    while (!stop_flag) {
+      asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]),"=r"(v[1]),"=r"(v[2]),"=r"(v[3]),"=r"(v[4]),"=r"(v[5]),"=r"(v[6]),"=r"(v[7]),"=r"(v[8]),"=r"(v[9]),"=r"(v[10]),"=r"(v[11]),"=r"(v[12]),"=r"(v[13]),"=r"(v[14]),"=r"(v[15])
+        : "r"(tmem + (((uint32_t)(warp & 3) * 32u) << 16) + 448u) : "memory");
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      acc += __uint_as_float(v[0]);
+    }
+    if (acc == 123.f) out[2] = 1;
+  } else if ((mode & 4) && warp == 6 && lane == 0) {
+    // TMA-like producer: 16 KB bulk copies global -> smem (a scratch region after the operands)
+    uint8_t* dst = smem + 4 * 16384 + 4 * 256 * 128;
+    uint32_t ph = 0;
+    while (!stop_flag) {
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(&cbar)), "r"(16384) : "memory");
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                   ::"r"(smem_u32(dst)), "l"(gsrc + (blockIdx.x * 1024)), "r"(16384), "r"(smem_u32(&cbar)) : "memory");
+      uint32_t ok = 0;
+      while (!ok) asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(&cbar)), "r"(ph) : "memory");
+      ph ^= 1;
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -72,26 +99,23 @@ __global__ void __launch_bounds__(128, 1) probe(int n_mma, int same_operands, lo
   }
 }
 template <int N, int NACC>
-void run(int same) {
+void run(int same, int mode = 0) {
   const int n_acc = NACC;
   long long* out; cudaMalloc(&out, 16);
-  const int smem = 4 * 16384 + 4 * 256 * 128 + 2048;
+  const int smem = 4 * 16384 + 4 * 256 * 128 + 16384 + 2048;
+  static uint4* gsrc = nullptr; if (!gsrc) { cudaMalloc(&gsrc, 148 * 16384); cudaMemset(gsrc, 1, 148 * 16384); }
   cudaFuncSetAttribute(probe<N, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   const int n = 2048;
-  probe<N, NACC><<<148, 128, smem>>>(n, same, out);
-  probe<N, NACC><<<148, 128, smem>>>(n, same, out);
+  probe<N, NACC><<<148, 256, smem>>>(n, same, out, mode, gsrc);
+  probe<N, NACC><<<148, 256, smem>>>(n, same, out, mode, gsrc);
   cudaError_t e = cudaDeviceSynchronize();
   long long h[2] = {0, 0};
   cudaMemcpy(h, out, 16, cudaMemcpyDeviceToHost);
-  printf("N=%3d acc=%d same_ops=%d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (ideal %d)  %s\n", N, n_acc, same,
+  printf("mode=%d N=%3d acc=%d same_ops=%d : issue %.1f cyc/MMA, complete %.1f cyc/MMA (ideal %d)  %s\n", mode, N, n_acc, same,
          (double)h[0] / n, (double)h[1] / n, N / 2, e == cudaSuccess ? "" : cudaGetErrorString(e));
   cudaFree(out);
 }
 int main() {
-  for (int same = 0; same < 2; ++same) {
-    run<16, 1>(same); run<32, 1>(same); run<64, 1>(same); run<64, 2>(same); run<64, 4>(same);
-    run<128, 1>(same); run<128, 2>(same); run<128, 4>(same);
-    run<256, 1>(same); run<256, 2>(same);
-  }
+  for (int mode = 0; mode < 8; ++mode) { run<64, 1>(0, mode); run<32, 1>(0, mode); run<128, 1>(0, mode); run<256, 1>(0, mode); }
   return 0;
 }
