@@ -115,6 +115,16 @@ class Recognizer:
         self.ctx.crops_to_input(t.data_ptr(), b, crnn_in.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
         return labels_to_text(self.predict_device(crnn_in).cpu().numpy(), self.alphabet)
 
+    def recognize(self, image):
+        """Recognize text from a single pre-cropped image (reference recognition.py:467-489): fit to
+        200x31 with zero fill (host, as upstream), gray conversion, then the CUDA CRNN."""
+        import cv2
+
+        image = tools.read_and_fit(filepath_or_array=image, width=TARGET_WIDTH, height=TARGET_HEIGHT, cval=0)
+        if image.ndim == 3 and image.shape[-1] == 3:
+            image = cv2.cvtColor(image, code=cv2.COLOR_RGB2GRAY)
+        return self.recognize_crops(np.ascontiguousarray(image.reshape(1, TARGET_HEIGHT, TARGET_WIDTH)))[0]
+
     def recognize_from_boxes_device(self, images_t, boxes, counts):
         """images_t (N,H,W,3) u8 CUDA; boxes (N,M,4,2) f32 CUDA; counts host ndarray -> labels (B,48) i32 CUDA."""
         counts = np.asarray(counts)

@@ -48,6 +48,37 @@ def adjust_boxes(boxes, scale=1, boxes_format="boxes"):
     raise NotImplementedError(f"Unsupported boxes format: {boxes_format}")
 
 
+def fit(image, width, height, cval=255, mode="letterbox", return_scale=False):
+    """tools.fit (reference tools.py:402-452): scale the image to fit ``width`` x ``height`` keeping
+    its aspect ratio, then letterbox (pad bottom/right with ``cval``) or crop.  Host-side like the
+    reference: it only serves the single-crop ``Recognizer.recognize`` API, which is off the hot path."""
+    import cv2
+
+    sx, sy = width / image.shape[1], height / image.shape[0]
+    if sx == 1 and sy == 1:
+        return (image, 1) if return_scale else image
+    if mode not in ("letterbox", "crop"):
+        raise NotImplementedError(f"Unsupported mode: {mode}")
+    use_width = (sx <= sy) if mode == "letterbox" else (sx >= sy)
+    if use_width:
+        scale, new_w, new_h = sx, width, sx * image.shape[0]
+    else:
+        scale, new_h, new_w = sy, height, sy * image.shape[1]
+    resized = cv2.resize(image, dsize=(int(new_w), int(new_h)))
+    if mode == "letterbox":
+        fitted = np.zeros((height, width, 3), dtype="uint8") + cval
+        fitted[: resized.shape[0], : resized.shape[1]] = resized[:height, :width]
+    else:
+        fitted = resized[:height, :width]
+    return (fitted, scale) if return_scale else fitted
+
+
+def read_and_fit(filepath_or_array, width, height, cval=255, mode="letterbox"):
+    """tools.read_and_fit (reference tools.py:455-481)."""
+    image = read(filepath_or_array) if isinstance(filepath_or_array, str) else filepath_or_array
+    return fit(image=image, width=width, height=height, cval=cval, mode=mode)
+
+
 def sha256sum(filename):
     """tools.sha256sum (reference tools.py:484-492)."""
     h = hashlib.sha256()

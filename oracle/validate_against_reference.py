@@ -54,7 +54,7 @@ def reference_tools():
     # annotations in adjust_boxes reference tx.Literal[...]; strip annotations instead of stubbing
     with open(os.path.join(REF, "keras_ocr", "tools.py")) as f:
         tree = ast.parse(f.read())
-    names = {"get_rotated_width_height", "warpBox", "get_rotated_box", "pad", "resize_image", "adjust_boxes", "fix_line"}
+    names = {"get_rotated_width_height", "warpBox", "get_rotated_box", "pad", "resize_image", "adjust_boxes", "fix_line", "fit"}
     body = []
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in names:
@@ -164,6 +164,16 @@ def check_inputs(tools, out):
         out[f"resize_{tag}_dst"] = ref
         out[f"resize_{tag}_params"] = np.array([scale, max_size, s_ref], np.float64)
         print(f"  resize/pad/gray {tag}: {img.shape} -> {ref.shape} scale {s_ref:.4f} identical")
+    from keras_ocr_b200 import tools as p_tools
+    for tag, (h, w, mode, cval) in {"wide": (40, 300, "letterbox", 0), "tall": (90, 120, "letterbox", 0), "crop": (50, 180, "crop", 255),
+                                     "exact": (31, 200, "letterbox", 0)}.items():
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = tools.fit(image=img, width=200, height=31, cval=cval, mode=mode)
+        assert np.array_equal(ref, p_tools.fit(img, 200, 31, cval=cval, mode=mode))
+        out[f"fit_{tag}_src"] = img
+        out[f"fit_{tag}_dst"] = ref
+        out[f"fit_{tag}_params"] = np.array([cval, 1 if mode == "crop" else 0])
+    print("  fit (letterbox / crop): identical")
     boxes = rng.uniform(0, 100, (5, 4, 2)).astype(np.float32)
     assert np.array_equal(tools.adjust_boxes(boxes=boxes, boxes_format="boxes", scale=0.5), boxes * 0.5)
 

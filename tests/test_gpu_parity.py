@@ -333,3 +333,53 @@ def test_blank_page_gives_no_predictions(cuda_device):
                     recognizer=Recognizer(weights=W.synthetic_crnn_weights(2)), scale=2)
     out = pipe.recognize([np.full((256, 256, 3), 255, np.uint8)])
     assert out == [[]]
+
+
+def test_pipeline_ragged_batch_max_size_and_injection(cuda_device):
+    """Different-sized inputs are resized per image (scale capped by max_size for the large one),
+    padded with 255 to the batch maximum (pipeline.py:44-57) and the boxes come back in each
+    image's own pixels; injecting this package's Detector/Recognizer into a *generic* Pipeline flow
+    (duck typing, pipeline.py:18-26) gives the same answer as the all-device flow."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import synth
+    from oracle.pipeline import OraclePipeline
+
+    cw, rw = W.synthetic_craft_weights(3, textlike=True), W.synthetic_crnn_weights(2)
+    rng = np.random.default_rng(33)
+    pages = [synth.text_image(rng, 192, 384, 4)[0], synth.text_image(rng, 160, 256, 2)[0], synth.text_image(rng, 256, 640, 4)[0]]
+    det, rec = Detector(weights=cw), Recognizer(weights=rw)
+    pipe = Pipeline(detector=det, recognizer=rec, scale=2, max_size=1024)     # 640 * 2 > 1024 -> scale 1.6 for page 3
+    got = pipe.recognize(pages)
+    ref = OraclePipeline(cw, rw, scale=2, max_size=1024).recognize(pages)
+    assert [len(g) for g in got] == [len(r) for r in ref]
+    for g, r in zip(got, ref):
+        for (tg, bg), (tr, br) in zip(g, r):
+            assert _match_quads(bg, br) <= 1.0
+
+    class Wrapped:                      # hides the native types -> Pipeline takes its generic (host array) path
+        def __init__(self, obj):
+            self.obj = obj
+        def detect(self, images, **kw):
+            return self.obj.detect(images, **kw)
+        def recognize_from_boxes(self, images, box_groups, **kw):
+            return self.obj.recognize_from_boxes(images, box_groups, **kw)
+    generic = Pipeline(detector=Wrapped(det), recognizer=Wrapped(rec), scale=2, max_size=1024).recognize(pages)
+    assert [[t for t, _ in g] for g in generic] == [[t for t, _ in g] for g in got]
+    for g, r in zip(generic, got):
+        for (_, bg), (_, br) in zip(g, r):
+            assert np.abs(bg - br).max() <= 1e-3
+
+
+def test_recognizer_single_crop_api(recognizer):
+    """Recognizer.recognize(image) (recognition.py:467-489) == recognize_from_boxes on the fitted crop."""
+    import cv2
+    from keras_ocr_b200 import tools
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (40, 260, 3), dtype=np.uint8)
+    text = recognizer.recognize(img)
+    fitted = tools.fit(img, 200, 31, cval=0)
+    gray = cv2.cvtColor(fitted, cv2.COLOR_RGB2GRAY)
+    assert text == recognizer.recognize_crops(gray[None])[0]
+    assert isinstance(text, str)
