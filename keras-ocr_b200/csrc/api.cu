@@ -1,5 +1,6 @@
 // api.cu -- C-ABI entry points (include/b2ocr.h): context, weight packing, network orchestration.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -186,6 +187,8 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   b2o_ctx* ctx = new b2o_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : 1;
+  if (const char* e = getenv("B2O_TC_STAGE_OUT")) ctx->tc_stage_out = atoi(e) ? 1 : 0;
   *out = ctx;
   return B2O_OK;
 }

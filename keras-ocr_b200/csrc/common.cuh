@@ -65,6 +65,8 @@ struct b2o_ctx {
   int device = 0;
   int sm_count = 148;
   int conv_engine = B2O_CONV_AUTO;
+  int tc_stage_out = 0;        // stage narrow fp16 output tiles in smem for coalesced stores (B2O_TC_STAGE_OUT=1; measured slower)
+  int tc_issuers = 1;          // MMA-issuing warps of conv_tc_kernel (2 = faster on small layers, not bit-reproducible)
   int64_t launches = 0;
   std::string error;
   std::map<std::string, ConvLayer> craft, crnn;

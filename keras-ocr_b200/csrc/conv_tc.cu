@@ -33,9 +33,14 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 608;          // warp0 TMA, warps 1-2 MMA issuers, warps 3..18 epilogue (4 per TMEM quadrant)
+// One MMA-issuing warp.  (Two issuers on alternate A stages were tried: +3 % on small-N layers, but the
+// order in which the two warps' MMAs reach the pipe -- hence the fp32 accumulation order -- then depends on
+// timing and results are no longer bit-reproducible run to run.  Determinism wins: ctx->tc_issuers = 1;
+// set B2O_TC_ISSUERS=2 in the environment to experiment.)
+constexpr int MAX_ISSUERS = 2;            // warps 1..2 are issuer slots; p.issuers of them are active (default 1)
+constexpr int NUM_THREADS = 32 * (1 + MAX_ISSUERS + 16);   // warp0 TMA, issuer slots, 16 epilogue warps (4 per TMEM quadrant)
 constexpr int EPI_THREADS = 512;
-constexpr int SMEM_TOTAL = 230 * 1024;     // dynamic shared memory we allow ourselves (max 227 KB = 232448 B)
+constexpr int SMEM_TOTAL = 227 * 1024;     // dynamic shared memory per CTA (the sm_100 maximum, 232448 B)
 constexpr int MAX_RING = 8;
 
 struct TcParams {
@@ -49,6 +54,9 @@ struct TcParams {
   int na, nb;                             // ring depths
   int a_stride, a_bytes;                  // bytes between A stages / bytes one A box delivers
   int off_b, off_bar;                     // shared-memory offsets
+  int group;                              // MODE 3: A stages per tile (p.na then counts groups)
+  int issuers;                            // active MMA-issuing warps (1 = bit-reproducible, 2 = experimental)
+  int stage_out, off_epi;                 // epilogue stages the fp16 tile in smem for coalesced row stores
   const float *s1, *t1, *s2, *t2;
   int relu;
   void* out;
@@ -204,7 +212,8 @@ struct TileIter {
 };
 
 // ------------------------------------------------------------------------------------------ kernel
-// MODE: 0 = generic tiles, 1 = halo tiles (3x3, dilation 1), 2 = halo tiles + resident filter bank
+// MODE: 0 = generic tiles, 1 = halo tiles (3x3, dilation 1), 2 = halo tiles + resident filter bank,
+//       3 = as 2 with all A stages of a tile on ONE mbarrier (one wait + one issue region per tile)
 template <int BLOCK_N, int KCH, int MODE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
@@ -218,6 +227,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   constexpr int ACC_STAGES = (512 / BLOCK_N) > 8 ? 8 : (512 / BLOCK_N);
   constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N) < 32 ? 32 : (ACC_STAGES * BLOCK_N);
   constexpr int CH = 16;                                   // accumulator columns per tcgen05.ld (per epilogue warp visit)
+  constexpr int EPI_PITCH = BLOCK_N * 2 + 16;              // bytes per staged output row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -245,7 +255,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
-      mbar_init(&tmem_full[s], 2);                       // one arrival per issuing warp
+      mbar_init(&tmem_full[s], static_cast<uint32_t>(p.issuers));   // one arrival per issuing warp
       mbar_init(&tmem_empty[s], EPI_THREADS);
       mbar_init(&order_bar[s], 1);
     }
@@ -271,7 +281,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   }
   constexpr uint32_t tmem_base = 0u;
 
-  constexpr bool HALO = MODE >= 1, RESIDENT = MODE == 2;
+  constexpr bool HALO = MODE >= 1, RESIDENT = MODE >= 2, GROUPED = MODE == 3;
   constexpr int TAPS_PER_A = HALO ? 3 : 1;                 // dy taps served by one A stage
   const int taps = p.ksize * p.ksize;
   const int kchunks = p.cin / KCH;
@@ -291,6 +301,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       const int groups = HALO ? 3 : taps;                  // dx positions (halo) or filter taps (generic)
       for (TileIter ti(p); ti.valid(); ti.next()) {
         const int tw0 = ti.c1 << p.bw_log2, th0 = ti.c2 << p.bh_log2, tn0 = ti.c3 << p.bn_log2, t_ntile = ti.c0;
+        if (GROUPED) {                                     // every A box of the tile lands on one barrier
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(p.group * p.a_bytes));
+          uint8_t* dst = smem_a + sa * p.group * p.a_stride;
+          for (int g = 0; g < 3; ++g)
+            for (int kc = 0; kc < kchunks; ++kc) {
+              tma_load_4d(&amap, &a_full[sa], dst, kc * KCH, tw0 + g - 1, th0 - 1, tn0);
+              dst += p.a_stride;
+            }
+          if (++sa == p.na) { sa = 0; pa ^= 1; }
+          continue;
+        }
         int ky = 0, kx = 0;
         for (int g = 0; g < groups; ++g) {
           const int ax = HALO ? (tw0 + g - 1) : (tw0 + (kx - half_k) * p.dil);
@@ -315,16 +337,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1 || warp == 2) {
-    // ===================================================================== MMA issuers (two warps)
-    // The tensor pipe accepts MMAs with (almost) no queue, so the ~80-100 cycles of scalar work an
-    // issuing warp spends per A stage (barrier wait, fences, descriptor arithmetic, commits) would
-    // leave it idle -- ruinous for small-N layers whose MMAs take only 48-64 cycles.  Two warps
-    // therefore take alternate A stages: one prepares while the other's MMAs execute.  Each warp
-    // runs warp-converged (uniform-register operands; only the tcgen05 instructions are predicated
-    // on one elected lane) and commits only the stages it issued (tcgen05.commit tracks the MMAs of
-    // the executing thread).  The accumulator-zeroing MMA of a tile belongs to the owner of the
-    // tile's first stage; the other warp waits on order_bar until it has been issued.
+  } else if (warp >= 1 && warp <= MAX_ISSUERS) {
+    if (warp <= p.issuers) {
+    // ===================================================================== MMA issuer
+    // The tensor pipe accepts MMAs with (almost) no queue, so every scalar instruction between two
+    // UTCHMMAs is exposed.  The issuing warp therefore runs warp-converged (descriptors, stage indices
+    // and the TMEM address stay in uniform registers; only the tcgen05 instructions are predicated on
+    // one elected lane) and issues all MMAs of an A stage from ONE elected region where it can.
+    // (The code is written for NUM_ISSUERS warps taking alternate A stages; see the note at NUM_ISSUERS.)
     constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                (static_cast<uint32_t>(BLOCK_M >> 4) << 24);   // D=f32, A=B=f16 K-major, N, M=128
     constexpr uint32_t TAP_DESC = TAP_SHIFT >> 4, B_DESC = B_BYTES >> 4;       // in 16-byte descriptor units
@@ -336,18 +356,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     int sa = 0, sb = 0, acc = 0;
     uint32_t pa = 0, pb = 0, acc_phase = 0, q = 0;          // q = global A-stage counter (ownership parity)
     const int groups = HALO ? 3 : taps;
+#ifdef B2O_TC_DEBUG
     long long dbg_t = 0, dbg_a = 0, dbg_b = 0, dbg_tiles = 0;
     const long long dbg_start = clock64();
+#define B2O_TIMED_WAIT(counter, stmt) { const long long c0_ = clock64(); stmt; counter += clock64() - c0_; }
+#else
+#define B2O_TIMED_WAIT(counter, stmt) { stmt; }
+#endif
+    if (GROUPED) {
+      // one wait and one elected region per tile: nothing but descriptor adds between the UTCHMMAs
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        mbar_wait(&a_full[sa], pa);
+        tcgen05_after_sync();
+        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+        if (elect_one()) {
+          uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa * p.group) * a_step);
+          uint32_t accumulate = 0;
+          for (int g = 0; g < 3; ++g)
+            for (int kc = 0; kc < kchunks; ++kc) {
+#pragma unroll
+              for (int t = 0; t < 3; ++t) {
+                const uint64_t bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>((t * 3 + g) * kchunks + kc) * B_DESC);
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                           accumulate);
+                  accumulate = 1;
+                }
+              }
+              adesc += a_step;
+            }
+          umma_commit(&a_empty[sa]);
+          umma_commit(&tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++sa == p.na) { sa = 0; pa ^= 1; }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+    } else
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      { const long long c0 = clock64(); mbar_wait(&tmem_empty[acc], acc_phase ^ 1); dbg_t += clock64() - c0; ++dbg_tiles; }
+      B2O_TIMED_WAIT(dbg_t, mbar_wait(&tmem_empty[acc], acc_phase ^ 1))
+#ifdef B2O_TC_DEBUG
+      ++dbg_tiles;
+#endif
       tcgen05_after_sync();
       const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-      const bool zero_owner = (static_cast<int>(q & 1u) == me);
+      const bool zero_owner = (static_cast<int>(q % static_cast<uint32_t>(p.issuers)) == me);
       bool need_order = !zero_owner, first = true, issued = false;
       for (int g = 0; g < groups; ++g) {
         for (int kc = 0; kc < kchunks; ++kc) {
-          if (static_cast<int>(q & 1u) == me) {
-            { const long long c0 = clock64(); mbar_wait(&a_full[sa], pa); dbg_a += clock64() - c0; }
+          if (static_cast<int>(q % static_cast<uint32_t>(p.issuers)) == me) {
+            B2O_TIMED_WAIT(dbg_a, mbar_wait(&a_full[sa], pa))
             if (need_order) { mbar_wait(&order_bar[acc], acc_phase); need_order = false; }
             const uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa) * a_step);
             const bool zeroing = first && zero_owner;      // this stage holds the tile's accumulator-zeroing MMA
@@ -359,7 +419,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
               for (int t = 0; t < TAPS_PER_A; ++t)
                 bdesc[t] = b_desc0 + static_cast<uint64_t>(
                                static_cast<uint32_t>(RESIDENT ? ((t * 3 + g) * kchunks + kc) : sb) * B_DESC);
-              if (!RESIDENT) { const long long c0 = clock64(); mbar_wait(&b_full[sb], pb); dbg_b += clock64() - c0; }
+              if (!RESIDENT) B2O_TIMED_WAIT(dbg_b, mbar_wait(&b_full[sb], pb))
               tcgen05_after_sync();
               if (elect_one()) {
 #pragma unroll
@@ -381,7 +441,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
               tcgen05_after_sync();
 #pragma unroll
               for (int t = 0; t < TAPS_PER_A; ++t) {
-                { const long long c0 = clock64(); mbar_wait(&b_full[sbl], pbl); dbg_b += clock64() - c0; }
+                B2O_TIMED_WAIT(dbg_b, mbar_wait(&b_full[sbl], pbl))
                 tcgen05_after_sync();
                 const uint64_t bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sbl) * B_DESC);
                 if (elect_one()) {
@@ -415,15 +475,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       __syncwarp();
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
+#ifdef B2O_TC_DEBUG
     if (lane == 0 && blockIdx.x < 160 && me == 0) {
       unsigned long long* d = g_tc_debug + blockIdx.x * 8;
       d[0] = static_cast<unsigned long long>(clock64() - dbg_start);
       d[1] = dbg_t; d[2] = dbg_a; d[3] = dbg_b; d[4] = dbg_tiles;
     }
+#endif
+#undef B2O_TIMED_WAIT
+    }
   } else {
     // ===================================================================== epilogue (warps 3..18)
     const int quad = warp & 3;                            // TMEM lane quadrant this warp may touch
-    const int sub = (warp - 3) >> 2;                      // the four warps of a quadrant split the column chunks
+    const int sub = (warp - 1 - MAX_ISSUERS) >> 2;                      // the four warps of a quadrant split the column chunks
     const int row = quad * 32 + lane;                     // accumulator row = pixel inside the tile
     const int bw_mask = (1 << p.bw_log2) - 1, bh_mask = (1 << p.bh_log2) - 1;
     const int wi = row & bw_mask;
@@ -489,7 +553,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             __half2 hv = __floats2half2_rn(y[j], y[j + 1]);
             pk[j / 2] = *reinterpret_cast<uint32_t*>(&hv);
           }
-          if (valid && p.write_full) {
+          if (p.stage_out) {
+            // park this thread's 16 channels in the quadrant's staging rows (pitch BLOCK_N*2+16 B: the
+            // 8 lanes of a store phase land in 8 different 16-byte bank groups)
+            uint8_t* srow = smem + p.off_epi + (quad * 32 + lane) * EPI_PITCH + ch * (CH * 2);
+#pragma unroll
+            for (int j = 0; j < CH / 2; j += 4)
+              *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+          } else if (valid && p.write_full) {
             __half* o = reinterpret_cast<__half*>(p.out) + pix * p.out_ld + c0;
 #pragma unroll
             for (int j = 0; j < CH / 2; j += 4)
@@ -516,7 +587,27 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         }
       }
       tcgen05_before_sync();
-      mbar_arrive(&tmem_empty[acc]);
+      mbar_arrive(&tmem_empty[acc]);                       // TMEM stage drained: the MMA warps may reuse it
+      if (p.stage_out) {
+        // the four warps of this quadrant now write its 32 pixel rows with row-contiguous 16-byte
+        // stores (a per-thread-row store touches 32 different 128 B lines per instruction)
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
+        constexpr int PIECES = BLOCK_N / 8;                // 16-byte pieces per pixel row
+        const uint8_t* sq = smem + p.off_epi + quad * 32 * EPI_PITCH;
+        for (int pc = sub * 32 + lane; pc < 32 * PIECES; pc += 128) {
+          const int rr = pc / PIECES, c8 = pc - rr * PIECES;
+          const int r2 = quad * 32 + rr;
+          const int w2 = (ti.c1 << p.bw_log2) + (r2 & bw_mask);
+          const int h2 = (ti.c2 << p.bh_log2) + ((r2 >> p.bw_log2) & bh_mask);
+          const int n2 = (ti.c3 << p.bn_log2) + (r2 >> (p.bw_log2 + p.bh_log2));
+          if (w2 < p.W && h2 < p.H && n2 < p.N) {
+            const size_t px2 = (static_cast<size_t>(n2) * p.H + h2) * p.W + w2;
+            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + px2 * p.out_ld + c_base + c8 * 8) =
+                *reinterpret_cast<const uint4*>(sq + rr * EPI_PITCH + c8 * 16);
+          }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");   // staging rows reusable
+      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -666,30 +757,43 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   p.total_tiles = static_cast<int>(total);
 
   // shared-memory plan: [A ring][B ring | resident filter bank][barriers]
-  const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/;
+  // staged (coalesced) output stores for fp16 full-tile writes of narrow layers
+  p.issuers = ctx->tc_issuers;
+  p.stage_out = (ctx->tc_stage_out && !out_f32 && write_full && bn <= 128) ? 1 : 0;
+  const int epi_bytes = p.stage_out ? (128 * (bn * 2 + 16) + 1023) / 1024 * 1024 : 0;
+  const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/ - epi_bytes;
   p.a_bytes = p.halo ? 18 * 8 * kch * 2 : 128 * kch * 2;
   p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
   const long long res_bytes = static_cast<long long>(taps) * kchunks * b_bytes;
   p.resident = (p.halo && p.n_tiles == 1 && res_bytes + 2LL * p.a_stride <= budget && res_bytes <= (1 << 20) - 1) ? 1 : 0;
   if (p.resident) {
     p.na = static_cast<int>((budget - res_bytes) / p.a_stride);
-    if (p.na > MAX_RING) p.na = MAX_RING;
+    const int n_a = 3 * kchunks;                           // A stages per tile
+    if (p.issuers == 1 && p.na >= 2 * n_a) {               // MODE 3: whole tiles per barrier
+      p.group = n_a;
+      p.na = p.na / n_a;
+      if (p.na > MAX_RING) p.na = MAX_RING;
+      p.off_b = p.na * n_a * p.a_stride;
+    } else {
+      if (p.na > MAX_RING) p.na = MAX_RING;
+      p.off_b = p.na * p.a_stride;
+    }
     p.nb = 1;
-    p.off_b = p.na * p.a_stride;
-    p.off_bar = p.off_b + static_cast<int>((res_bytes + 1023) / 1024 * 1024);
+    p.off_epi = p.off_b + static_cast<int>((res_bytes + 1023) / 1024 * 1024);
   } else if (p.halo) {
     p.na = b_bytes <= 16384 ? 4 : 3;
     p.nb = (budget - p.na * p.a_stride) / b_bytes;
     if (p.nb > MAX_RING) p.nb = MAX_RING;
     p.off_b = p.na * p.a_stride;
-    p.off_bar = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
+    p.off_epi = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
   } else {
     int s = budget / (p.a_stride + b_bytes);
     if (s > MAX_RING) s = MAX_RING;
     p.na = p.nb = s;
     p.off_b = p.na * p.a_stride;
-    p.off_bar = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
+    p.off_epi = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
   }
+  p.off_bar = p.off_epi + epi_bytes;
   if (p.na < 2 || p.nb < 1) { ctx->set_error("conv_tc_run: shared-memory plan failed for " + L.name); return B2O_ERR_ARG; }
   int smem_bytes = p.off_bar + 512 + 1024;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;    // one CTA per SM (TMEM base 0, see kernel)
@@ -722,6 +826,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   }
 #define B2O_TC_CASE(BN, KC)                                                            \
   if (bn == BN && kch == KC) {                                                         \
+    if (p.resident && p.group) return launch<BN, KC, 3>(ctx, amap, L, p, smem_bytes, st); \
     if (p.resident) return launch<BN, KC, 2>(ctx, amap, L, p, smem_bytes, st);         \
     if (p.halo) return launch<BN, KC, 1>(ctx, amap, L, p, smem_bytes, st);             \
     return launch<BN, KC, 0>(ctx, amap, L, p, smem_bytes, st);                         \

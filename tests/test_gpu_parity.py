@@ -372,6 +372,23 @@ def test_pipeline_ragged_batch_max_size_and_injection(cuda_device):
             assert np.abs(bg - br).max() <= 1e-3
 
 
+def test_results_are_bit_reproducible(detector, recognizer):
+    """Same inputs -> bit-identical scores and labels on every call (fixed MMA accumulation order)."""
+    rng = np.random.default_rng(12)
+    img = torch.from_numpy(rng.integers(0, 256, (2, 160, 224, 3), dtype=np.uint8)).to(detector.device)
+    a = detector.predict_device(img).clone()
+    for _ in range(3):
+        assert torch.equal(detector.predict_device(img), a)
+    crops = torch.from_numpy(rng.integers(0, 256, (24, 31, 200), dtype=np.uint8)).to(recognizer.device)
+    x = torch.empty((24, 200, 31), dtype=torch.float16, device=recognizer.device)
+    recognizer.ctx.crops_to_input(crops.data_ptr(), 24, x.data_ptr(), _stream())
+    la = recognizer.predict_device(x).clone()
+    logits = recognizer.tap("logits", (24, 48, 37), torch.float32).clone()
+    for _ in range(3):
+        assert torch.equal(recognizer.predict_device(x), la)
+        assert torch.equal(recognizer.tap("logits", (24, 48, 37), torch.float32), logits)
+
+
 def test_recognizer_single_crop_api(recognizer):
     """Recognizer.recognize(image) (recognition.py:467-489) == recognize_from_boxes on the fitted crop."""
     import cv2
