@@ -135,7 +135,7 @@ CraftPlan plan_craft(int n, int h, int w) {
   p.off_u2b = take(p.h8, p.w8, 128); p.off_u3a = take(p.h4, p.w4, 128); p.off_u3b = take(p.h4, p.w4, 64);
   p.off_u4a = take(p.h2, p.w2, 64); p.off_u4b = take(p.h2, p.w2, 32); p.off_h1 = take(p.h2, p.w2, 32);
   p.off_h2 = take(p.h2, p.w2, 32); p.off_h3 = take(p.h2, p.w2, 16);
-  p.off_x16 = take(p.h1, p.w1, 16);       // normalised input, 3 -> 16 channels, for the tensor-core stem
+  p.off_x16 = take(p.h1, p.w1, 32);       // normalised 3x3 im2col of the input (27 -> 32 channels) for the tensor-core stem
   p.bytes = off;
   return p;
 }
@@ -188,7 +188,6 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : 1;
-  if (const char* e = getenv("B2O_TC_STAGE_OUT")) ctx->tc_stage_out = atoi(e) ? 1 : 0;
   *out = ctx;
   return B2O_OK;
 }
@@ -269,6 +268,14 @@ extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
       };
       ConvLayer& L16 = ctx->craft["stem16"];
       B2O_RETURN_IF(build_layer(ctx, L16, "stem16", 16, s.cout, s.k, 1, s.relu, wget16, s1, t1, nullptr, nullptr, false));
+      // ... and as a 1x1 convolution over the 27(+5)-channel im2col of the input (the production stem)
+      auto wget32 = [wd, cin, k](int o, int c, int, int) {
+        if (c >= 27) return 0.0f;
+        const int tap = c / 3, ch = c % 3;
+        return wd[((static_cast<size_t>(o) * cin + ch) * k + tap / 3) * k + tap % 3];
+      };
+      ConvLayer& L32 = ctx->craft["stem32"];
+      B2O_RETURN_IF(build_layer(ctx, L32, "stem32", 32, s.cout, 1, 1, s.relu, wget32, s1, t1, nullptr, nullptr, false));
     }
   }
   ctx->craft_loaded = true;
@@ -415,12 +422,16 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
   const TensorView h1 = V(p.off_h1, p.h2, p.w2, 32), h2 = V(p.off_h2, p.h2, p.w2, 32), h3 = V(p.off_h3, p.h2, p.w2, 16);
 
   // encoder (detection.py:312-324); taps s1..s4 are written straight into the concat buffers
-  if (ctx->conv_engine == B2O_CONV_SIMT || L("stem16").block_n == 0) {
+  if (ctx->conv_engine == B2O_CONV_SIMT || L("stem32").block_n == 0) {
     B2O_RETURN_IF(stem_rgb_run(ctx, L("basenet.slice1.0"), img, n, h, w, a, st));          // fp32 CUDA-core stem
-  } else {
+  } else if (ctx->conv_engine == B2O_CONV_TC_GENERIC) {                                      // 3x3 over 16 padded channels
     const TensorView x16 = V(p.off_x16, p.h1, p.w1, 16);
     B2O_RETURN_IF(normalize16_run(ctx, img, n, h, w, x16.ptr, st));
     B2O_RETURN_IF(conv_run(ctx, L("stem16"), x16, a, 0, st));
+  } else {                                                                                   // 1x1 over the 27-ch im2col
+    const TensorView x32 = V(p.off_x16, p.h1, p.w1, 32);
+    B2O_RETURN_IF(im2col27_run(ctx, img, n, h, w, x32.ptr, st));
+    B2O_RETURN_IF(conv_run(ctx, L("stem32"), x32, a, 0, st));
   }
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.3"), a, b, 0, st, &p1, 0));     // conv + fused 2x2 max pool
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.7"), p1, c, 0, st));

@@ -24,14 +24,35 @@ struct Component {                       // one kept connected component
   int root, x, y, w, h, area;
 };
 
-__global__ void binarize_kernel(const float* __restrict__ scores, long long total, int hw, float text_thr,
+// cv2.threshold x2 + union mask + label init.  A pixel's initial label is the start of its horizontal run
+// inside the warp's 32-pixel segment (ballot + clz), so row runs need no union at all except across
+// segment boundaries -- this removes >90 % of the atomics of the merge pass.
+__global__ void binarize_kernel(const float* __restrict__ scores, long long total, int hw, int ws, float text_thr,
                                 float link_thr, uint8_t* __restrict__ mask, int* __restrict__ label) {
   const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  bool fg = false, both = false;
+  int q = 0, row = -1;
+  if (p < total) {
+    const float2 s = reinterpret_cast<const float2*>(scores)[p];
+    const bool t = s.x > text_thr, l = s.y > link_thr;
+    fg = t || l; both = t && l;
+    q = static_cast<int>(p % hw);
+    row = static_cast<int>(p / ws);                       // global row id (image * hs + y)
+  }
+  const uint32_t same_row = __match_any_sync(0xffffffffu, row);
+  const uint32_t m = __ballot_sync(0xffffffffu, fg) & same_row;
   if (p >= total) return;
-  const float2 s = reinterpret_cast<const float2*>(scores)[p];
-  const bool t = s.x > text_thr, l = s.y > link_thr;
-  mask[p] = static_cast<uint8_t>((t || l) ? (1 | ((t && l) ? 2 : 0)) : 0);
-  label[p] = (t || l) ? static_cast<int>(p % hw) : -1;
+  int lab = -1, run = 0;
+  if (fg) {
+    const uint32_t below = (lane == 0) ? 0u : (m << (32 - lane));   // bit (lane-1) -> bit 31
+    run = __clz(~below);                                           // consecutive foreground pixels to the left
+    if (run > lane) run = lane;
+    lab = q - run;
+  }
+  // mask bits: 1 = foreground, 2 = text & link, 4 = first pixel of its run inside this 32-pixel segment
+  mask[p] = static_cast<uint8_t>(fg ? (1 | (both ? 2 : 0) | (run == 0 ? 4 : 0)) : 0);
+  label[p] = lab;
 }
 
 __device__ __forceinline__ int uf_find(const int* L, int a) {
@@ -63,8 +84,14 @@ __global__ void merge_kernel(const uint8_t* __restrict__ mask, int* __restrict__
   const int q = static_cast<int>(p % hw);
   const int x = q % ws, y = q / ws;
   int* L = label + static_cast<size_t>(img) * hw;
-  if (x > 0 && (mask[p - 1] & 1)) uf_unite(L, q, q - 1);
-  if (y > 0 && (mask[p - ws] & 1)) uf_unite(L, q, q - ws);
+  const bool left = x > 0 && (mask[p - 1] & 1);
+  // horizontal: only where the warp-segment run labelling of binarize_kernel could not see the neighbour
+  if (left && (mask[p] & 4)) uf_unite(L, q, q - 1);
+  // vertical: once per pair of overlapping runs (if left and up-left are foreground, `left` already did it)
+  if (y > 0 && (mask[p - ws] & 1)) {
+    const bool upleft = x > 0 && (mask[p - ws - 1] & 1);
+    if (!(left && upleft)) uf_unite(L, q, q - ws);
+  }
 }
 
 __global__ void flatten_kernel(int* __restrict__ label, long long total, int hw) {
@@ -598,8 +625,8 @@ extern "C" int b2o_get_boxes(b2o_ctx* ctx, const float* scores, int n, int hs, i
   B2O_CUDA_CHECK(ctx, cudaMemsetAsync(w.st.maxy, 0xff, px * 4, st));
   B2O_CUDA_CHECK(ctx, cudaMemsetAsync(w.st.maxtext, 0x80, px * 4, st));  // very negative key
   B2O_CUDA_CHECK(ctx, cudaMemsetAsync(w.big_locks, 0, static_cast<size_t>(n) * 4, st));
-  binarize_kernel<<<nblocks(total, 256), 256, 0, st>>>(scores, total, hs * ws, text_threshold, link_threshold, w.mask,
-                                                      w.label);
+  binarize_kernel<<<nblocks(total, 256), 256, 0, st>>>(scores, total, hs * ws, ws, text_threshold, link_threshold,
+                                                      w.mask, w.label);
   B2O_LAUNCH_CHECK(ctx);
   merge_kernel<<<nblocks(total, 256), 256, 0, st>>>(w.mask, w.label, total, hs, ws);
   B2O_LAUNCH_CHECK(ctx);

@@ -65,7 +65,6 @@ struct b2o_ctx {
   int device = 0;
   int sm_count = 148;
   int conv_engine = B2O_CONV_AUTO;
-  int tc_stage_out = 0;        // stage narrow fp16 output tiles in smem for coalesced stores (B2O_TC_STAGE_OUT=1; measured slower)
   int tc_issuers = 1;          // MMA-issuing warps of conv_tc_kernel (2 = faster on small layers, not bit-reproducible)
   int64_t launches = 0;
   std::string error;
@@ -94,6 +93,7 @@ int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Tenso
              int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1);
 int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, int h, int w,
                  const TensorView& out, cudaStream_t st);
+int im2col27_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st);
 int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st);
 int stem_crnn_run(b2o_ctx* ctx, const ConvLayer& L, const __half* x, int b, const TensorView& out,
                   cudaStream_t st);

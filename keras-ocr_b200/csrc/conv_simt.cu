@@ -396,6 +396,49 @@ int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, in
   return B2O_OK;
 }
 
+// compute_input + 3x3 im2col: every pixel gets its 27 normalised neighbour values (zero outside the image,
+// i.e. "same" padding of the normalised input) in 32 fp16 channels, k = (ky*3+kx)*3 + c.  The stem conv
+// then is a 1x1 convolution with K = 32: ONE 64-byte-row TMA box and two MMAs per 128-pixel tile (the
+// 16-channel 3x3 formulation needed 432 32-byte TMA rows per tile and was bound by the TMA row rate).
+__global__ void im2col27_kernel(const uint8_t* __restrict__ img, int N, int H, int W, __half* __restrict__ out) {
+  const long long total = static_cast<long long>(N) * H * W;
+  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (p >= total) return;
+  const int w = static_cast<int>(p % W);
+  const int h = static_cast<int>((p / W) % H);
+  const int n = static_cast<int>(p / (static_cast<long long>(W) * H));
+  const double mean[3] = {0.485 * 255, 0.456 * 255, 0.406 * 255};
+  const double stdv[3] = {0.229 * 255, 0.224 * 255, 0.225 * 255};
+  __half v[32];
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int ih = h + ky - 1, iw = w + kx - 1;
+      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+      const uint8_t* ip = img + ((static_cast<size_t>(n) * H + (ok ? ih : 0)) * W + (ok ? iw : 0)) * 3;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        float t = static_cast<float>(static_cast<double>(ip[c]) - mean[c]);
+        t = static_cast<float>(static_cast<double>(t) / stdv[c]);
+        v[(ky * 3 + kx) * 3 + c] = __float2half_rn(ok ? t : 0.0f);
+      }
+    }
+#pragma unroll
+  for (int k = 27; k < 32; ++k) v[k] = __float2half_rn(0.0f);
+  uint4* o = reinterpret_cast<uint4*>(out + p * 32);
+  const uint4* s = reinterpret_cast<const uint4*>(v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) o[i] = s[i];
+}
+
+int im2col27_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st) {
+  const long long total = static_cast<long long>(n) * h * w;
+  im2col27_kernel<<<blocks_for(total, 256), 256, 0, st>>>(img, n, h, w, out);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
 int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st) {
   const long long total = static_cast<long long>(n) * h * w;
   normalize16_kernel<<<blocks_for(total, 256), 256, 0, st>>>(img, total, out);

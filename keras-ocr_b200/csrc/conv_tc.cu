@@ -56,7 +56,6 @@ struct TcParams {
   int off_b, off_bar;                     // shared-memory offsets
   int group;                              // MODE 3: A stages per tile (p.na then counts groups)
   int issuers;                            // active MMA-issuing warps (1 = bit-reproducible, 2 = experimental)
-  int stage_out, off_epi;                 // epilogue stages the fp16 tile in smem for coalesced row stores
   const float *s1, *t1, *s2, *t2;
   int relu;
   void* out;
@@ -226,8 +225,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   // throughput; with 4-8 the MMA warp runs several tiles ahead of the epilogue warps.
   constexpr int ACC_STAGES = (512 / BLOCK_N) > 8 ? 8 : (512 / BLOCK_N);
   constexpr int TMEM_COLS = (ACC_STAGES * BLOCK_N) < 32 ? 32 : (ACC_STAGES * BLOCK_N);
+  // Epilogue work split.  N = 256 (2 accumulator stages): the four warps of a TMEM quadrant share every tile,
+  // each taking every 4th 16-column chunk.  N <= 128 (>= 4 stages): each of the four warps takes every 4th
+  // TILE whole -- the per-tile fixed cost (barrier wake-up, coordinates, scale/shift loads) is then paid once
+  // per four tiles per warp, which is what bounds short-K layers.
+  constexpr bool TILE_PAR = ACC_STAGES >= 4;
   constexpr int CH = 16;                                   // accumulator columns per tcgen05.ld (per epilogue warp visit)
-  constexpr int EPI_PITCH = BLOCK_N * 2 + 16;              // bytes per staged output row
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
@@ -256,7 +259,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&tmem_full[s], static_cast<uint32_t>(p.issuers));   // one arrival per issuing warp
-      mbar_init(&tmem_empty[s], EPI_THREADS);
+      mbar_init(&tmem_empty[s], TILE_PAR ? 128 : EPI_THREADS);
       mbar_init(&order_bar[s], 1);
     }
     mbar_init(res_full, 1);
@@ -495,7 +498,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     const int ni = row >> (p.bw_log2 + p.bh_log2);
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (TileIter ti(p); ti.valid(); ti.next()) {
+    int tile_seq = 0;
+    for (TileIter ti(p); ti.valid(); ti.next(), ++tile_seq) {
+      if (TILE_PAR && (tile_seq & 3) != sub) {             // another warp of this quadrant owns the tile
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
       const int w = (ti.c1 << p.bw_log2) + wi, h = (ti.c2 << p.bh_log2) + hi, n = (ti.c3 << p.bn_log2) + ni;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
@@ -509,7 +517,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
 #pragma unroll 1
-      for (int ch = sub; ch < BLOCK_N / CH; ch += 4) {
+      for (int ch = TILE_PAR ? 0 : sub; ch < BLOCK_N / CH; ch += TILE_PAR ? 1 : 4) {
         uint32_t v[CH];
         tmem_ld<CH>(taddr + static_cast<uint32_t>(ch * CH), v);
         tmem_ld_wait();
@@ -553,14 +561,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             __half2 hv = __floats2half2_rn(y[j], y[j + 1]);
             pk[j / 2] = *reinterpret_cast<uint32_t*>(&hv);
           }
-          if (p.stage_out) {
-            // park this thread's 16 channels in the quadrant's staging rows (pitch BLOCK_N*2+16 B: the
-            // 8 lanes of a store phase land in 8 different 16-byte bank groups)
-            uint8_t* srow = smem + p.off_epi + (quad * 32 + lane) * EPI_PITCH + ch * (CH * 2);
-#pragma unroll
-            for (int j = 0; j < CH / 2; j += 4)
-              *reinterpret_cast<uint4*>(srow + 4 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
-          } else if (valid && p.write_full) {
+          if (valid && p.write_full) {
             __half* o = reinterpret_cast<__half*>(p.out) + pix * p.out_ld + c0;
 #pragma unroll
             for (int j = 0; j < CH / 2; j += 4)
@@ -588,26 +589,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       }
       tcgen05_before_sync();
       mbar_arrive(&tmem_empty[acc]);                       // TMEM stage drained: the MMA warps may reuse it
-      if (p.stage_out) {
-        // the four warps of this quadrant now write its 32 pixel rows with row-contiguous 16-byte
-        // stores (a per-thread-row store touches 32 different 128 B lines per instruction)
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");
-        constexpr int PIECES = BLOCK_N / 8;                // 16-byte pieces per pixel row
-        const uint8_t* sq = smem + p.off_epi + quad * 32 * EPI_PITCH;
-        for (int pc = sub * 32 + lane; pc < 32 * PIECES; pc += 128) {
-          const int rr = pc / PIECES, c8 = pc - rr * PIECES;
-          const int r2 = quad * 32 + rr;
-          const int w2 = (ti.c1 << p.bw_log2) + (r2 & bw_mask);
-          const int h2 = (ti.c2 << p.bh_log2) + ((r2 >> p.bw_log2) & bh_mask);
-          const int n2 = (ti.c3 << p.bn_log2) + (r2 >> (p.bw_log2 + p.bh_log2));
-          if (w2 < p.W && h2 < p.H && n2 < p.N) {
-            const size_t px2 = (static_cast<size_t>(n2) * p.H + h2) * p.W + w2;
-            *reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.out) + px2 * p.out_ld + c_base + c8 * 8) =
-                *reinterpret_cast<const uint4*>(sq + rr * EPI_PITCH + c8 * 16);
-          }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(1 + quad) : "memory");   // staging rows reusable
-      }
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -698,7 +679,7 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
   int bn = 256;
   while (bn > 16 && (L.cout % bn != 0)) bn >>= 1;
   if (L.cout % bn != 0) return B2O_OK;
-  if (L.kch == 32 && bn > 32) return B2O_OK;               // instantiated combinations only
+  if (L.kch == 32 && bn > 64) return B2O_OK;               // instantiated combinations only
   if (L.kch == 16 && bn != 32 && bn != 64) return B2O_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return B2O_ERR_CUDA; }
@@ -757,11 +738,8 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   p.total_tiles = static_cast<int>(total);
 
   // shared-memory plan: [A ring][B ring | resident filter bank][barriers]
-  // staged (coalesced) output stores for fp16 full-tile writes of narrow layers
   p.issuers = ctx->tc_issuers;
-  p.stage_out = (ctx->tc_stage_out && !out_f32 && write_full && bn <= 128) ? 1 : 0;
-  const int epi_bytes = p.stage_out ? (128 * (bn * 2 + 16) + 1023) / 1024 * 1024 : 0;
-  const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/ - epi_bytes;
+  const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/;
   p.a_bytes = p.halo ? 18 * 8 * kch * 2 : 128 * kch * 2;
   p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
   const long long res_bytes = static_cast<long long>(taps) * kchunks * b_bytes;
@@ -779,21 +757,20 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
       p.off_b = p.na * p.a_stride;
     }
     p.nb = 1;
-    p.off_epi = p.off_b + static_cast<int>((res_bytes + 1023) / 1024 * 1024);
+    p.off_bar = p.off_b + static_cast<int>((res_bytes + 1023) / 1024 * 1024);
   } else if (p.halo) {
     p.na = b_bytes <= 16384 ? 4 : 3;
     p.nb = (budget - p.na * p.a_stride) / b_bytes;
     if (p.nb > MAX_RING) p.nb = MAX_RING;
     p.off_b = p.na * p.a_stride;
-    p.off_epi = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
+    p.off_bar = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
   } else {
     int s = budget / (p.a_stride + b_bytes);
     if (s > MAX_RING) s = MAX_RING;
     p.na = p.nb = s;
     p.off_b = p.na * p.a_stride;
-    p.off_epi = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
+    p.off_bar = p.off_b + (p.nb * b_bytes + 1023) / 1024 * 1024;
   }
-  p.off_bar = p.off_epi + epi_bytes;
   if (p.na < 2 || p.nb < 1) { ctx->set_error("conv_tc_run: shared-memory plan failed for " + L.name); return B2O_ERR_ARG; }
   int smem_bytes = p.off_bar + 512 + 1024;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;    // one CTA per SM (TMEM base 0, see kernel)
@@ -832,7 +809,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
     return launch<BN, KC, 0>(ctx, amap, L, p, smem_bytes, st);                         \
   }
   B2O_TC_CASE(16, 64); B2O_TC_CASE(32, 64); B2O_TC_CASE(64, 64); B2O_TC_CASE(128, 64); B2O_TC_CASE(256, 64);
-  B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32);
+  B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32); B2O_TC_CASE(64, 32);
   B2O_TC_CASE(32, 16); B2O_TC_CASE(64, 16);
 #undef B2O_TC_CASE
   ctx->set_error("conv_tc_run: no kernel instance for " + L.name);
