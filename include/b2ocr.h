@@ -38,6 +38,10 @@ typedef enum {
   B2O_ERR_STATE = -5       /* call needs weights that were not loaded                         */
 } b2o_status;
 
+/* Largest CTC class count (len(alphabet) + 1, recognition.py:376-381) the recognizer accepts; the class
+ * count itself is read from the shape of "fc_12.kernel" (256, K) at b2o_load_crnn.                */
+#define B2O_MAX_CLASSES 1024
+
 /* One named float32 host tensor (row-major) of a checkpoint, in the reference's naming:
  * CRAFT: PyTorch keys of craft_mlt_25k.pth without the "module." prefix (detection.py:428-468);
  * CRNN : Keras layer names of build_model (recognition.py:214-329), Keras layouts.            */
@@ -115,7 +119,7 @@ int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in_dev, int b, int32_t* labe
 
 /* Debug / test taps (not on the product path): copy an intermediate of the last forward pass.
  * b2o_crnn_tap names: "features" (b,50,7,512 f16), "theta" (b,6 f32), "warped" (b,50,7,512 f16),
- * "fc_9" (b,50,128 f16), "l1" (b,50,128 f16), "l2" (b,50,256 f16), "logits" (b,48,37 f32).     */
+ * "fc_9" (b,50,128 f16), "l1" (b,50,128 f16), "l2" (b,50,256 f16), "logits" (b,48,K f32).      */
 int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws_dev, int b, void* out_dev,
                  size_t out_bytes, void* stream);
 

@@ -13,6 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libb2ocr.so")
 
 CONV_AUTO, CONV_SIMT, CONV_TC_GENERIC = 0, 1, 2
+MAX_CLASSES = 1024            # B2O_MAX_CLASSES in include/b2ocr.h
 
 
 class B2OError(RuntimeError):

@@ -135,7 +135,7 @@ CraftPlan plan_craft(int n, int h, int w) {
   p.off_u2b = take(p.h8, p.w8, 128); p.off_u3a = take(p.h4, p.w4, 128); p.off_u3b = take(p.h4, p.w4, 64);
   p.off_u4a = take(p.h2, p.w2, 64); p.off_u4b = take(p.h2, p.w2, 32); p.off_h1 = take(p.h2, p.w2, 32);
   p.off_h2 = take(p.h2, p.w2, 32); p.off_h3 = take(p.h2, p.w2, 16);
-  p.off_x16 = take(p.h1, p.w1, 32);       // normalised 3x3 im2col of the input (27 -> 32 channels) for the tensor-core stem
+  p.off_x16 = take(p.h1, p.w1, 16);       // normalised input, 3 -> 16 channels, for the tensor-core stem
   p.bytes = off;
   return p;
 }
@@ -159,7 +159,7 @@ CrnnPlan plan_crnn(int b) {
   p.off_theta = take(B * 6 * 4); p.off_warp = take(B * 50 * 7 * 512 * 2); p.off_fc9 = take(B * 50 * 128 * 2);
   p.off_xw1 = take(B * 50 * 1024 * 4); p.off_hf = take(B * 50 * 128 * 2); p.off_hb = take(B * 50 * 128 * 2);
   p.off_l1 = take(B * 50 * 128 * 2); p.off_xw2 = take(B * 50 * 1024 * 4); p.off_l2 = take(B * 50 * 256 * 2);
-  p.off_logits = take(B * 48 * 37 * 4);
+  p.off_logits = take(B * 48 * B2O_MAX_CLASSES * 4);   // sized for the largest alphabet so the plan is context-free
   p.bytes = off;
   return p;
 }
@@ -268,14 +268,6 @@ extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
       };
       ConvLayer& L16 = ctx->craft["stem16"];
       B2O_RETURN_IF(build_layer(ctx, L16, "stem16", 16, s.cout, s.k, 1, s.relu, wget16, s1, t1, nullptr, nullptr, false));
-      // ... and as a 1x1 convolution over the 27(+5)-channel im2col of the input (the production stem)
-      auto wget32 = [wd, cin, k](int o, int c, int, int) {
-        if (c >= 27) return 0.0f;
-        const int tap = c / 3, ch = c % 3;
-        return wd[((static_cast<size_t>(o) * cin + ch) * k + tap / 3) * k + tap % 3];
-      };
-      ConvLayer& L32 = ctx->craft["stem32"];
-      B2O_RETURN_IF(build_layer(ctx, L32, "stem32", 32, s.cout, 1, 1, s.relu, wget32, s1, t1, nullptr, nullptr, false));
     }
   }
   ctx->craft_loaded = true;
@@ -371,13 +363,18 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
     }
   }
   {
-    const int64_t wshape[2] = {256, 37};
-    const int64_t vshape[1] = {37};
+    // Dense(len(alphabet)+1) (recognition.py:322-327, 376-381): the class count comes from the tensor itself
+    auto fc = m.find("fc_12.kernel");
+    const int64_t K = fc != m.end() && fc->second->ndim == 2 ? fc->second->shape[1] : 0;
+    if (K < 2 || K > B2O_MAX_CLASSES) { ctx->set_error("fc_12.kernel must be (256, K) with 2 <= K <= 1024"); return B2O_ERR_WEIGHTS; }
+    const int64_t wshape[2] = {256, K};
+    const int64_t vshape[1] = {K};
     const b2o_tensor* w = need(ctx, m, "fc_12.kernel", 2, wshape);
     const b2o_tensor* b = need(ctx, m, "fc_12.bias", 1, vshape);
     if (!w || !b) return B2O_ERR_WEIGHTS;
-    if (!(ctx->fc12_w = dev_upload(ctx, tovec(w, 256 * 37)))) return B2O_ERR_CUDA;
-    if (!(ctx->fc12_b = dev_upload(ctx, tovec(b, 37)))) return B2O_ERR_CUDA;
+    if (!(ctx->fc12_w = dev_upload(ctx, tovec(w, 256 * K)))) return B2O_ERR_CUDA;
+    if (!(ctx->fc12_b = dev_upload(ctx, tovec(b, K)))) return B2O_ERR_CUDA;
+    ctx->n_classes = static_cast<int>(K);
   }
   ctx->crnn_loaded = true;
   return B2O_OK;
@@ -422,16 +419,12 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
   const TensorView h1 = V(p.off_h1, p.h2, p.w2, 32), h2 = V(p.off_h2, p.h2, p.w2, 32), h3 = V(p.off_h3, p.h2, p.w2, 16);
 
   // encoder (detection.py:312-324); taps s1..s4 are written straight into the concat buffers
-  if (ctx->conv_engine == B2O_CONV_SIMT || L("stem32").block_n == 0) {
+  if (ctx->conv_engine == B2O_CONV_SIMT || L("stem16").block_n == 0) {
     B2O_RETURN_IF(stem_rgb_run(ctx, L("basenet.slice1.0"), img, n, h, w, a, st));          // fp32 CUDA-core stem
-  } else if (ctx->conv_engine == B2O_CONV_TC_GENERIC) {                                      // 3x3 over 16 padded channels
+  } else {
     const TensorView x16 = V(p.off_x16, p.h1, p.w1, 16);
     B2O_RETURN_IF(normalize16_run(ctx, img, n, h, w, x16.ptr, st));
     B2O_RETURN_IF(conv_run(ctx, L("stem16"), x16, a, 0, st));
-  } else {                                                                                   // 1x1 over the 27-ch im2col
-    const TensorView x32 = V(p.off_x16, p.h1, p.w1, 32);
-    B2O_RETURN_IF(im2col27_run(ctx, img, n, h, w, x32.ptr, st));
-    B2O_RETURN_IF(conv_run(ctx, L("stem32"), x32, a, 0, st));
   }
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.3"), a, b, 0, st, &p1, 0));     // conv + fused 2x2 max pool
   B2O_RETURN_IF(conv_run(ctx, L("basenet.slice1.7"), p1, c, 0, st));
@@ -541,7 +534,7 @@ extern "C" int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws, int 
   else if (s == "fc_9") { off = p.off_fc9; bytes = B * 50 * 128 * 2; }
   else if (s == "l1") { off = p.off_l1; bytes = B * 50 * 128 * 2; }
   else if (s == "l2") { off = p.off_l2; bytes = B * 50 * 256 * 2; }
-  else if (s == "logits") { off = p.off_logits; bytes = B * 48 * 37 * 4; }
+  else if (s == "logits") { off = p.off_logits; bytes = B * 48 * ctx->n_classes * 4; }
   else { ctx->set_error("b2o_crnn_tap: unknown tap " + s); return B2O_ERR_ARG; }
   if (out_bytes < bytes) { ctx->set_error("b2o_crnn_tap: output too small"); return B2O_ERR_ARG; }
   B2O_CUDA_CHECK(ctx, cudaMemcpyAsync(out, reinterpret_cast<const uint8_t*>(ws) + off, bytes, cudaMemcpyDeviceToDevice,

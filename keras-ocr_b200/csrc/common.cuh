@@ -73,7 +73,8 @@ struct b2o_ctx {
   // CRNN tail parameters (device)
   float *stn_d2_w = nullptr, *stn_d2_b = nullptr;              // dense 64 -> 6, fp32
   __half* lstm_u[4] = {nullptr, nullptr, nullptr, nullptr};    // recurrent kernels [128][512] fp16
-  float *fc12_w = nullptr, *fc12_b = nullptr;                  // [256][37], [37] fp32
+  float *fc12_w = nullptr, *fc12_b = nullptr;                  // [256][K], [K] fp32, K = len(alphabet) + 1
+  int n_classes = 37;                                          // K (last index = CTC blank), <= B2O_MAX_CLASSES
   std::vector<void*> owned;    // device allocations freed in b2o_destroy
   // optional per-launch timing of the tensor-core conv kernel (bench.py's roofline leg)
   bool profile = false;
@@ -93,7 +94,6 @@ int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Tenso
              int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1);
 int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, int h, int w,
                  const TensorView& out, cudaStream_t st);
-int im2col27_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st);
 int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st);
 int stem_crnn_run(b2o_ctx* ctx, const ConvLayer& L, const __half* x, int b, const TensorView& out,
                   cudaStream_t st);

@@ -312,6 +312,61 @@ __global__ void upsample_kernel(const __half* __restrict__ in, int in_ld, int N,
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(op) * out_ld + cv * 8) = r;
 }
 
+// Exact 2x case (OH == 2*IH, OW == 2*IW; every CRAFT decoder level when the input is a multiple of 32):
+// one thread per (quad, 8-channel vector).  Quad (qy, qx) in [0, IH] x [0, IW] sits between input rows
+// qy-1 / qy and columns qx-1 / qx (clamped) and produces output rows 2qy-1, 2qy and columns 2qx-1, 2qx
+// from ONE set of four loads.  Weights are those of upsample_kernel (0.25 / 0.75, and 0 on the first
+// row/column where the source coordinate clamps to 0), and the expression has the same form, so both
+// kernels give identical bits.
+__global__ void upsample2x_kernel(const __half* __restrict__ in, int in_ld, int N, int IH, int IW, int C,
+                                  __half* __restrict__ out, int out_ld) {
+  const int CV = C / 8;
+  const int QW = IW + 1, QH = IH + 1;
+  const long long total = static_cast<long long>(N) * QH * QW * CV;
+  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int cv = static_cast<int>(idx % CV);
+  const long long q = idx / CV;
+  const int qx = static_cast<int>(q % QW);
+  const int qy = static_cast<int>((q / QW) % QH);
+  const int n = static_cast<int>(q / (static_cast<long long>(QW) * QH));
+  const int ya = max(qy - 1, 0), yb = min(qy, IH - 1);
+  const int xa = max(qx - 1, 0), xb = min(qx, IW - 1);
+  const __half* base = in + static_cast<size_t>(n) * IH * IW * in_ld + cv * 8;
+  const uint4 a = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(ya) * IW + xa) * in_ld);
+  const uint4 b = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(ya) * IW + xb) * in_ld);
+  const uint4 c = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(yb) * IW + xa) * in_ld);
+  const uint4 d = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(yb) * IW + xb) * in_ld);
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+  const __half2* pc = reinterpret_cast<const __half2*>(&c);
+  const __half2* pd = reinterpret_cast<const __half2*>(&d);
+  const int OH = 2 * IH, OW = 2 * IW;
+#pragma unroll
+  for (int ry = 0; ry < 2; ++ry) {
+    const int oh = 2 * qy - 1 + ry;
+    if (oh < 0 || oh >= OH) continue;
+    const float ly = ry == 0 ? 0.25f : (qy == 0 ? 0.0f : 0.75f), hy = 1.0f - ly;
+#pragma unroll
+    for (int rx = 0; rx < 2; ++rx) {
+      const int ow = 2 * qx - 1 + rx;
+      if (ow < 0 || ow >= OW) continue;
+      const float lx = rx == 0 ? 0.25f : (qx == 0 ? 0.0f : 0.75f), hx = 1.0f - lx;
+      uint4 r;
+      __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 fa = __half22float2(pa[i]), fb = __half22float2(pb[i]);
+        const float2 fc = __half22float2(pc[i]), fd = __half22float2(pd[i]);
+        const float vx = hy * (hx * fa.x + lx * fb.x) + ly * (hx * fc.x + lx * fd.x);
+        const float vy = hy * (hx * fa.y + lx * fb.y) + ly * (hx * fc.y + lx * fd.y);
+        pr[i] = __floats2half2_rn(vx, vy);
+      }
+      *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oh) * OW + ow) * out_ld + cv * 8) = r;
+    }
+  }
+}
+
 // conv_cls.6 (16->16, ReLU) + conv_cls.8 (16->2, linear): fp32 scores (n,h,w,2).
 __global__ void __launch_bounds__(256)
 head_tail_kernel(const __half* __restrict__ in, int in_ld, long long total, const float* __restrict__ w6 /*[16][16]*/,
@@ -396,49 +451,6 @@ int stem_rgb_run(b2o_ctx* ctx, const ConvLayer& L, const uint8_t* img, int n, in
   return B2O_OK;
 }
 
-// compute_input + 3x3 im2col: every pixel gets its 27 normalised neighbour values (zero outside the image,
-// i.e. "same" padding of the normalised input) in 32 fp16 channels, k = (ky*3+kx)*3 + c.  The stem conv
-// then is a 1x1 convolution with K = 32: ONE 64-byte-row TMA box and two MMAs per 128-pixel tile (the
-// 16-channel 3x3 formulation needed 432 32-byte TMA rows per tile and was bound by the TMA row rate).
-__global__ void im2col27_kernel(const uint8_t* __restrict__ img, int N, int H, int W, __half* __restrict__ out) {
-  const long long total = static_cast<long long>(N) * H * W;
-  const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  const int w = static_cast<int>(p % W);
-  const int h = static_cast<int>((p / W) % H);
-  const int n = static_cast<int>(p / (static_cast<long long>(W) * H));
-  const double mean[3] = {0.485 * 255, 0.456 * 255, 0.406 * 255};
-  const double stdv[3] = {0.229 * 255, 0.224 * 255, 0.225 * 255};
-  __half v[32];
-#pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
-#pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ih = h + ky - 1, iw = w + kx - 1;
-      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-      const uint8_t* ip = img + ((static_cast<size_t>(n) * H + (ok ? ih : 0)) * W + (ok ? iw : 0)) * 3;
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        float t = static_cast<float>(static_cast<double>(ip[c]) - mean[c]);
-        t = static_cast<float>(static_cast<double>(t) / stdv[c]);
-        v[(ky * 3 + kx) * 3 + c] = __float2half_rn(ok ? t : 0.0f);
-      }
-    }
-#pragma unroll
-  for (int k = 27; k < 32; ++k) v[k] = __float2half_rn(0.0f);
-  uint4* o = reinterpret_cast<uint4*>(out + p * 32);
-  const uint4* s = reinterpret_cast<const uint4*>(v);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) o[i] = s[i];
-}
-
-int im2col27_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st) {
-  const long long total = static_cast<long long>(n) * h * w;
-  im2col27_kernel<<<blocks_for(total, 256), 256, 0, st>>>(img, n, h, w, out);
-  B2O_LAUNCH_CHECK(ctx);
-  return B2O_OK;
-}
-
 int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __half* out, cudaStream_t st) {
   const long long total = static_cast<long long>(n) * h * w;
   normalize16_kernel<<<blocks_for(total, 256), 256, 0, st>>>(img, total, out);
@@ -469,6 +481,12 @@ int maxpool3s1_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cu
 }
 
 int upsample_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cudaStream_t st) {
+  if (out.h == 2 * in.h && out.w == 2 * in.w) {
+    const long long quads = static_cast<long long>(in.n) * (in.h + 1) * (in.w + 1) * (in.c / 8);
+    upsample2x_kernel<<<blocks_for(quads, 256), 256, 0, st>>>(in.ptr, in.ld, in.n, in.h, in.w, in.c, out.ptr, out.ld);
+    B2O_LAUNCH_CHECK(ctx);
+    return B2O_OK;
+  }
   const long long total = static_cast<long long>(out.n) * out.h * out.w * (in.c / 8);
   upsample_kernel<<<blocks_for(total, 256), 256, 0, st>>>(in.ptr, in.ld, in.n, in.h, in.w, in.c, out.ptr, out.ld,
                                                           out.h, out.w);

@@ -60,6 +60,7 @@ struct TcParams {
   int relu;
   void* out;
   int out_ld, out_f32, write_full;
+  int wide;                 // output rows are 32-byte aligned: one 256-bit store per 16 fp16 channels (full sector)
   __half* pool_out;                       // fused 2x2/2 max-pool output (or null)
   int pool_ld, PH, PW;
 };
@@ -177,6 +178,13 @@ __device__ __forceinline__ void tmem_ld<16>(uint32_t taddr, uint32_t* v) {
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr)
       : "memory");
+}
+// 256-bit global store (sm_100: STG.E.256).  A lane's 16 fp16 channels are one whole 32-byte sector; two
+// 128-bit stores touch the same sector twice (ncu: 32 sectors per request, half of each written per pass).
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ bool elect_one() {
@@ -550,9 +558,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         if (p.out_f32) {
           if (valid) {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + c0;
+            if (p.wide) {
 #pragma unroll
-            for (int j = 0; j < CH; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+              for (int j = 0; j < CH; j += 8) st_global_256(o + j, reinterpret_cast<const uint32_t*>(y + j));
+            } else {
+#pragma unroll
+              for (int j = 0; j < CH; j += 4)
+                *reinterpret_cast<float4*>(o + j) = make_float4(y[j], y[j + 1], y[j + 2], y[j + 3]);
+            }
           }
         } else {
           uint32_t pk[CH / 2];
@@ -563,9 +576,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
           }
           if (valid && p.write_full) {
             __half* o = reinterpret_cast<__half*>(p.out) + pix * p.out_ld + c0;
+            if (p.wide) {
+              st_global_256(o, pk);
+            } else {
 #pragma unroll
-            for (int j = 0; j < CH / 2; j += 4)
-              *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+              for (int j = 0; j < CH / 2; j += 4)
+                *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+            }
           }
           if (p.pool_out != nullptr) {                    // warp-uniform branch
 #pragma unroll
@@ -580,9 +597,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             }
             if (pool_writer) {
               __half* o = p.pool_out + ppix * p.pool_ld + c0;
+              if (p.wide) {
+                st_global_256(o, pk);
+              } else {
 #pragma unroll
-              for (int j = 0; j < CH / 2; j += 4)
-                *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+                for (int j = 0; j < CH / 2; j += 4)
+                  *reinterpret_cast<uint4*>(o + 2 * j) = make_uint4(pk[j], pk[j + 1], pk[j + 2], pk[j + 3]);
+              }
             }
           }
         }
@@ -679,7 +700,7 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
   int bn = 256;
   while (bn > 16 && (L.cout % bn != 0)) bn >>= 1;
   if (L.cout % bn != 0) return B2O_OK;
-  if (L.kch == 32 && bn > 64) return B2O_OK;               // instantiated combinations only
+  if (L.kch == 32 && bn > 32) return B2O_OK;               // instantiated combinations only
   if (L.kch == 16 && bn != 32 && bn != 64) return B2O_OK;
   EncodeTiledFn enc = get_encode();
   if (!enc) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return B2O_ERR_CUDA; }
@@ -784,6 +805,11 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
     }
     p.pool_out = pool_out->ptr; p.pool_ld = pool_out->ld; p.PH = pool_out->h; p.PW = pool_out->w;
   }
+  {
+    const size_t esz = out_f32 ? 4 : 2;
+    p.wide = reinterpret_cast<uintptr_t>(out.ptr) % 32 == 0 && (out.ld * esz) % 32 == 0;
+    if (want_pool) p.wide = p.wide && reinterpret_cast<uintptr_t>(pool_out->ptr) % 32 == 0 && (pool_out->ld * 2) % 32 == 0;
+  }
 
   CUtensorMap amap;
   cuuint64_t dims[4] = {static_cast<cuuint64_t>(in.c), static_cast<cuuint64_t>(in.w), static_cast<cuuint64_t>(in.h),
@@ -809,7 +835,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
     return launch<BN, KC, 0>(ctx, amap, L, p, smem_bytes, st);                         \
   }
   B2O_TC_CASE(16, 64); B2O_TC_CASE(32, 64); B2O_TC_CASE(64, 64); B2O_TC_CASE(128, 64); B2O_TC_CASE(256, 64);
-  B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32); B2O_TC_CASE(64, 32);
+  B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32);
   B2O_TC_CASE(32, 16); B2O_TC_CASE(64, 16);
 #undef B2O_TC_CASE
   ctx->set_error("conv_tc_run: no kernel instance for " + L.name);

@@ -147,45 +147,65 @@ __global__ void add_kernel(const __half2* __restrict__ a, const __half2* __restr
 }
 
 // ---------------------------------------------------------------------------------------- fc_12 + CTC
-constexpr int kClasses = 37, kKeep = 48, kDiscard = 2, kFeat = 256;
+constexpr int kKeep = 48, kDiscard = 2, kFeat = 256, kFcWarps = 8, kStepsPerWarp = kKeep / kFcWarps;
 
-__global__ void __launch_bounds__(64)
-fc_ctc_kernel(const __half* __restrict__ l2 /*[B][50][256]*/, const float* __restrict__ w /*[256][37]*/,
-              const float* __restrict__ bias, int B, float* __restrict__ logits /*[B][48][37] or null*/,
+// One CTA per crop, one warp per 6 kept time steps; lane l owns classes l, l+32, ... (K = len(alphabet)+1 is a
+// run-time value: recognition.py:376-381 sizes the Dense layer from the alphabet).  Every logit is the same
+// serial fmaf chain over the 256 features in ascending order whatever K is; the argmax keeps the first maximum
+// (np.argmax / tf.argmax tie rule) and the collapse drops blanks (index K-1) and repeats.
+__global__ void __launch_bounds__(32 * kFcWarps)
+fc_ctc_kernel(const __half* __restrict__ l2 /*[B][50][256]*/, const float* __restrict__ w /*[256][K]*/,
+              const float* __restrict__ bias, int B, int K, float* __restrict__ logits /*[B][48][K] or null*/,
               int* __restrict__ labels /*[B][48]*/) {
   __shared__ int best[kKeep];
+  __shared__ __half xs[kKeep][kFeat];
   const int b = blockIdx.x;
-  const int t = threadIdx.x;                       // one thread per kept time step
-  if (t < kKeep) {
-    const __half* x = l2 + (static_cast<size_t>(b) * kSteps + t + kDiscard) * kFeat;
-    float acc[kClasses];
-#pragma unroll
-    for (int k = 0; k < kClasses; ++k) acc[k] = bias[k];
-    for (int c = 0; c < kFeat; ++c) {
-      const float xv = __half2float(x[c]);
-      const float* wr = w + c * kClasses;
-#pragma unroll
-      for (int k = 0; k < kClasses; ++k) acc[k] = fmaf(xv, __ldg(wr + k), acc[k]);
-    }
-    int arg = 0;
-    float mx = acc[0];
-#pragma unroll
-    for (int k = 1; k < kClasses; ++k)
-      if (acc[k] > mx) { mx = acc[k]; arg = k; }   // first maximum wins
-    best[t] = arg;
-    if (logits) {
-      float* lo = logits + (static_cast<size_t>(b) * kKeep + t) * kClasses;
-#pragma unroll
-      for (int k = 0; k < kClasses; ++k) lo[k] = acc[k];
-    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    const uint4* src = reinterpret_cast<const uint4*>(l2 + (static_cast<size_t>(b) * kSteps + kDiscard) * kFeat);
+    uint4* dst = reinterpret_cast<uint4*>(&xs[0][0]);
+    for (int i = threadIdx.x; i < kKeep * kFeat / 8; i += blockDim.x) dst[i] = src[i];
   }
   __syncthreads();
-  if (t == 0) {
+  const int t0 = warp * kStepsPerWarp;
+  float mx[kStepsPerWarp];
+  int arg[kStepsPerWarp];
+#pragma unroll
+  for (int j = 0; j < kStepsPerWarp; ++j) { mx[j] = -INFINITY; arg[j] = 0x7fffffff; }
+  for (int k = lane; k < K; k += 32) {
+    float acc[kStepsPerWarp];
+    const float bk = bias[k];
+#pragma unroll
+    for (int j = 0; j < kStepsPerWarp; ++j) acc[j] = bk;
+#pragma unroll 4
+    for (int c = 0; c < kFeat; ++c) {
+      const float wv = __ldg(w + static_cast<size_t>(c) * K + k);
+#pragma unroll
+      for (int j = 0; j < kStepsPerWarp; ++j) acc[j] = fmaf(__half2float(xs[t0 + j][c]), wv, acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < kStepsPerWarp; ++j) {
+      if (acc[j] > mx[j]) { mx[j] = acc[j]; arg[j] = k; }            // ascending k: first maximum wins
+      if (logits) logits[(static_cast<size_t>(b) * kKeep + t0 + j) * K + k] = acc[j];
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < kStepsPerWarp; ++j) {
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx[j], off);
+      const int oa = __shfl_xor_sync(0xffffffffu, arg[j], off);
+      if (om > mx[j] || (om == mx[j] && oa < arg[j])) { mx[j] = om; arg[j] = oa; }
+    }
+    if (lane == 0) best[t0 + j] = arg[j] == 0x7fffffff ? 0 : arg[j];  // all-NaN row: argmax returns 0
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     int* o = labels + static_cast<size_t>(b) * kKeep;
     int n = 0, prev = -1;
     for (int s = 0; s < kKeep; ++s) {
       const int c = best[s];
-      if (c != kClasses - 1 && c != prev) o[n++] = c;
+      if (c != K - 1 && c != prev) o[n++] = c;
       prev = c;
     }
     for (; n < kKeep; ++n) o[n] = -1;
@@ -225,7 +245,7 @@ int add_run(b2o_ctx* ctx, const __half* a, const __half* b, __half* o, long long
 }
 
 int fc_ctc_run(b2o_ctx* ctx, const __half* l2, int B, float* logits, int* labels, cudaStream_t st) {
-  fc_ctc_kernel<<<B, 64, 0, st>>>(l2, ctx->fc12_w, ctx->fc12_b, B, logits, labels);
+  fc_ctc_kernel<<<B, 32 * kFcWarps, 0, st>>>(l2, ctx->fc12_w, ctx->fc12_b, B, ctx->n_classes, logits, labels);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

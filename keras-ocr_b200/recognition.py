@@ -32,7 +32,10 @@ class Recognizer:
     """A text recognizer using the CRNN architecture, running as sm_100a CUDA kernels.
 
     Args:
-        alphabet: only the default ``0-9a-z`` alphabet is built (the kernels fix 37 classes).
+        alphabet: the characters the model recognises (default ``0-9a-z``; up to 1023 characters).  The
+            checkpoint's ``fc_12`` must have ``len(alphabet) + 1`` classes; if it does not, the reference's
+            "backbone weights only" behaviour applies (recognition.py:399-411): the top layer is
+            re-initialised (Glorot uniform, zero bias) and has to be trained before it is useful.
         weights: ``"kurapan"`` needs a converted ``crnn_kurapan.npz`` in the cache dir (Keras ``.h5``
             cannot be read without h5py); otherwise a ``.npz`` path or a dict keyed like ``weights.py``.
         build_params: must be ``None`` / the defaults (reference recognition.py:13-23).
@@ -40,13 +43,13 @@ class Recognizer:
 
     def __init__(self, alphabet=None, weights="kurapan", build_params=None, device=None):
         assert alphabet or weights, "At least one of alphabet or weights must be provided."
-        if alphabet is not None and alphabet != DEFAULT_ALPHABET:
-            raise NotImplementedError("only the default alphabet is supported by the CUDA recognizer")
         if build_params is not None:
             raise NotImplementedError("only DEFAULT_BUILD_PARAMS are supported by the CUDA recognizer")
         if not torch.cuda.is_available():
             raise _lib.B2OError("keras-ocr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
-        self.alphabet = DEFAULT_ALPHABET
+        self.alphabet = alphabet or DEFAULT_ALPHABET              # recognition.py:369-375
+        if len(self.alphabet) + 1 > _lib.MAX_CLASSES:
+            raise ValueError(f"alphabet too long: at most {_lib.MAX_CLASSES - 1} characters")
         self.blank_label_idx = len(self.alphabet)
         self.device_index = torch.cuda.current_device() if device is None else int(device)
         self.device = torch.device("cuda", self.device_index)
@@ -58,6 +61,14 @@ class Recognizer:
             tensors = weights_mod.load_npz(tools.find_cached("crnn_kurapan.npz"))
         else:
             raise NotImplementedError(f"Cannot load weights from {weights}")
+        n_classes = len(self.alphabet) + 1
+        top = tensors.get("fc_12.kernel")
+        if top is None or tuple(np.shape(top)) != (256, n_classes):
+            print("Provided alphabet does not match pretrained alphabet. Using backbone weights only.")
+            tensors = dict(tensors)
+            limit = float(np.sqrt(6.0 / (256 + n_classes)))           # keras Dense default: glorot_uniform, zeros
+            tensors["fc_12.kernel"] = np.random.default_rng(0).uniform(-limit, limit, (256, n_classes)).astype(np.float32)
+            tensors["fc_12.bias"] = np.zeros(n_classes, np.float32)
         self.ctx = _lib.Context(self.device_index)
         self.ctx.load_crnn(tensors)
         self.keep_workspace = False      # tests set this to read intermediate taps

@@ -143,8 +143,8 @@ def synthetic_craft_weights(seed=0, textlike=False):
     return w
 
 
-def synthetic_crnn_weights(seed=1):
-    """Seeded CRNN weights keyed by Keras layer name (Keras layouts)."""
+def synthetic_crnn_weights(seed=1, alphabet=ALPHABET):
+    """Seeded CRNN weights keyed by Keras layer name (Keras layouts); the top layer has len(alphabet)+1 classes."""
     rng = np.random.default_rng(seed)
     w = {}
     for name, cin, cout, k, bn in CRNN_CONVS:
@@ -172,8 +172,8 @@ def synthetic_crnn_weights(seed=1):
         b = (rng.standard_normal(512) * 0.05).astype(np.float32)
         b[128:256] += 1.0                                   # unit_forget_bias
         w[name + ".bias"] = b
-    w["fc_12.kernel"] = _he(rng, (256, len(ALPHABET) + 1), 256, 8.0)
-    w["fc_12.bias"] = (rng.standard_normal(len(ALPHABET) + 1) * 0.1).astype(np.float32)
+    w["fc_12.kernel"] = _he(rng, (256, len(alphabet) + 1), 256, 8.0)
+    w["fc_12.bias"] = (rng.standard_normal(len(alphabet) + 1) * 0.1).astype(np.float32)
     return w
 
 

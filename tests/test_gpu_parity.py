@@ -277,6 +277,50 @@ def test_ctc_collapse_exact(recognizer):
     assert np.array_equal(labels, expect)                      # integer work: bit-exact
 
 
+@pytest.mark.parametrize("alphabet", ["ab", "".join(chr(c) for c in range(32, 127)),
+                                      "".join(chr(c) for c in range(0x4E00, 0x4E00 + 300))])
+def test_custom_alphabet(cuda_device, alphabet):
+    """recognition.py:362-381: the class count follows the alphabet (K = 3, 96, 301).  Logits against the fp32
+    oracle within the CRNN tolerance; the device's greedy CTC equals the collapse of its own logits exactly;
+    strings use the caller's alphabet."""
+    from keras_ocr_b200 import weights as W
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import crnn, synth
+    w = W.synthetic_crnn_weights(5, alphabet=alphabet)
+    rec = Recognizer(alphabet=alphabet, weights=w)
+    assert rec.alphabet == alphabet and rec.blank_label_idx == len(alphabet)
+    rec.keep_workspace = True
+    rng = np.random.default_rng(4)
+    crops = np.stack([synth.noise_gray(rng, 31, 200) for _ in range(6)])
+    t = torch.from_numpy(crops).to(rec.device)
+    crnn_in = torch.empty((6, 200, 31), dtype=torch.float16, device=rec.device)
+    rec.ctx.crops_to_input(t.data_ptr(), 6, crnn_in.data_ptr(), _stream())
+    labels = rec.predict_device(crnn_in).cpu().numpy()
+    K = len(alphabet) + 1
+    logits = rec.tap("logits", (6, 48, K), torch.float32).cpu()
+    assert np.array_equal(labels, crnn.ctc_greedy(torch.softmax(logits, -1)))
+    l2 = rec.tap("l2", (6, 50, 256), torch.float16).float().cpu()[:, 2:]
+    own = l2 @ torch.from_numpy(w["fc_12.kernel"]) + torch.from_numpy(w["fc_12.bias"])
+    assert float((logits - own).abs().max()) <= 2e-3          # the Dense layer alone: fp32 on both sides
+    with torch.no_grad():
+        probs, inter = crnn.crnn_logits(w, crops.astype(np.float32) / 255, return_intermediates=True)
+    assert float((logits - inter["logits"]).abs().max()) <= 0.15
+    texts = rec.recognize_crops(crops)
+    assert texts == crnn.labels_to_text(labels, alphabet)
+    assert all(set(tx) <= set(alphabet) for tx in texts)
+
+
+def test_alphabet_mismatch_uses_backbone_only(cuda_device, capsys):
+    """recognition.py:399-411: a checkpoint whose top layer does not fit the alphabet keeps the backbone and
+    gets a freshly initialised top (same message as the reference)."""
+    from keras_ocr_b200 import weights as W
+    from keras_ocr_b200.recognition import Recognizer
+    rec = Recognizer(alphabet="xyz", weights=W.synthetic_crnn_weights(2))
+    assert "Using backbone weights only" in capsys.readouterr().out
+    out = rec.recognize_crops(np.zeros((2, 31, 200), np.uint8))
+    assert len(out) == 2 and all(set(tx) <= set("xyz") for tx in out)
+
+
 # ------------------------------------------------------------------------------- API behaviour
 def test_reference_api_contract(detector, recognizer):
     rng = np.random.default_rng(0)

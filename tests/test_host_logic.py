@@ -31,6 +31,14 @@ def test_labels_to_text_matches_reference_rule():
     ref = ["".join(DEFAULT_ALPHABET[i] for i in row if i not in (36, -1)) for row in rows]
     assert labels_to_text(rows) == ref
     assert labels_to_text(np.zeros((0, 48), np.int32)) == []
+    for alphabet in ("ab", "".join(chr(c) for c in range(32, 127)), "αβγδ漢字"):   # custom alphabets (ascii LUT and generic path)
+        blank = len(alphabet)
+        rows = np.full((16, 48), -1, np.int32)
+        for r in rows:
+            k = rng.integers(0, 30)
+            r[:k] = rng.integers(0, blank, k)
+        ref = ["".join(alphabet[i] for i in row if i not in (blank, -1)) for row in rows]
+        assert labels_to_text(rows, alphabet) == ref
 
 
 def test_adjust_boxes_and_read_contracts(tmp_path):
