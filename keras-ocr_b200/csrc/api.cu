@@ -187,7 +187,7 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   b2o_ctx* ctx = new b2o_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : 1;
+  if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : (atoi(e) == 1 ? 1 : 0);
   *out = ctx;
   return B2O_OK;
 }

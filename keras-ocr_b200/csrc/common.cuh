@@ -65,7 +65,7 @@ struct b2o_ctx {
   int device = 0;
   int sm_count = 148;
   int conv_engine = B2O_CONV_AUTO;
-  int tc_issuers = 1;          // MMA-issuing warps of conv_tc_kernel (2 = faster on small layers, not bit-reproducible)
+  int tc_issuers = 0;          // MMA-issuing warps of conv_tc_kernel: 0 = auto (2 for N <= 128 tiles), 1, 2
   int64_t launches = 0;
   std::string error;
   std::map<std::string, ConvLayer> craft, crnn;

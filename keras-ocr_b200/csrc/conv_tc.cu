@@ -33,11 +33,15 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int UMMA_K = 16;
-// One MMA-issuing warp.  (Two issuers on alternate A stages were tried: +3 % on small-N layers, but the
-// order in which the two warps' MMAs reach the pipe -- hence the fp32 accumulation order -- then depends on
-// timing and results are no longer bit-reproducible run to run.  Determinism wins: ctx->tc_issuers = 1;
-// set B2O_TC_ISSUERS=2 in the environment to experiment.)
-constexpr int MAX_ISSUERS = 2;            // warps 1..2 are issuer slots; p.issuers of them are active (default 1)
+// MMA-issuing warps: one, except in MODE 3 (one A slot per tile) with N <= 128, where two warps take alternate
+// TILES -- the scalar code of one warp (barrier waits, descriptor arithmetic) hides behind the other warp's
+// MMAs.  Every accumulator is fed by exactly one warp in program order, so the fp32 accumulation order is
+// fixed (two warps on alternate A stages of the SAME tile were tried first: faster too, but not
+// bit-reproducible run to run).  The A ring and the TMEM ring then have an even number of slots, so each slot
+// has ONE consumer: an mbarrier parity wait is only sound when the waiter is at most one phase behind, which
+// a warp skipping the other warp's stages in a shared ring is not (that variant dead-locked).
+// B2O_TC_ISSUERS=1 in the environment forces a single issuer.
+constexpr int MAX_ISSUERS = 2;            // warps 1..2 are issuer slots; p.issuers of them are active
 constexpr int NUM_THREADS = 32 * (1 + MAX_ISSUERS + 16);   // warp0 TMA, issuer slots, 16 epilogue warps (4 per TMEM quadrant)
 constexpr int EPI_THREADS = 512;
 constexpr int SMEM_TOTAL = 227 * 1024;     // dynamic shared memory per CTA (the sm_100 maximum, 232448 B)
@@ -55,7 +59,7 @@ struct TcParams {
   int a_stride, a_bytes;                  // bytes between A stages / bytes one A box delivers
   int off_b, off_bar;                     // shared-memory offsets
   int group;                              // MODE 3: A stages per tile (p.na then counts groups)
-  int issuers;                            // active MMA-issuing warps (1 = bit-reproducible, 2 = experimental)
+  int issuers;                            // active MMA-issuing warps (2 = alternate tiles)
   const float *s1, *t1, *s2, *t2;
   int relu;
   void* out;
@@ -266,7 +270,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       mbar_init(&b_empty[s], 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
-      mbar_init(&tmem_full[s], static_cast<uint32_t>(p.issuers));   // one arrival per issuing warp
+      mbar_init(&tmem_full[s], 1);                          // the commit of the warp that issued the tile
       mbar_init(&tmem_empty[s], TILE_PAR ? 128 : EPI_THREADS);
       mbar_init(&order_bar[s], 1);
     }
@@ -365,8 +369,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     const uint32_t a_step = static_cast<uint32_t>(p.a_stride) >> 4;
     if (RESIDENT) { mbar_wait(res_full, 0); tcgen05_after_sync(); }
     int sa = 0, sb = 0, acc = 0;
-    uint32_t pa = 0, pb = 0, acc_phase = 0, q = 0;          // q = global A-stage counter (ownership parity)
+    uint32_t pa = 0, pb = 0, acc_phase = 0;
     const int groups = HALO ? 3 : taps;
+    // With two issuing warps the warps take alternate TILES: every accumulator is fed by one warp in program
+    // order (bit-reproducible), and while one warp runs its per-stage scalar code (barrier wait, descriptor
+    // arithmetic: ~500 cycles per stage, which the queue-less tensor pipe would otherwise sit idle through)
+    // the other warp's MMAs keep the pipe busy.  A skipped tile only advances the ring positions.
+    const bool alternate = GROUPED && ACC_STAGES >= 4 && p.issuers == 2;
+    const int a_per_tile = GROUPED ? 1 : groups * kchunks;
+    const int b_per_tile = RESIDENT ? 0 : a_per_tile * TAPS_PER_A;
+    int tile_seq = 0;
 #ifdef B2O_TC_DEBUG
     long long dbg_t = 0, dbg_a = 0, dbg_b = 0, dbg_tiles = 0;
     const long long dbg_start = clock64();
@@ -374,13 +386,26 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
 #else
 #define B2O_TIMED_WAIT(counter, stmt) { stmt; }
 #endif
-    if (GROUPED) {
-      // one wait and one elected region per tile: nothing but descriptor adds between the UTCHMMAs
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        mbar_wait(&a_full[sa], pa);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_seq) {
+      if (alternate && (tile_seq & 1) != me) {             // the other warp's tile
+        sa += a_per_tile;
+        while (sa >= p.na) { sa -= p.na; pa ^= 1; }
+        if (!RESIDENT) {
+          sb += b_per_tile;
+          while (sb >= p.nb) { sb -= p.nb; pb ^= 1; }
+        }
+        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
+      }
+      B2O_TIMED_WAIT(dbg_t, mbar_wait(&tmem_empty[acc], acc_phase ^ 1))
+#ifdef B2O_TC_DEBUG
+      ++dbg_tiles;
+#endif
+      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+      if (GROUPED) {
+        // one wait and one elected region per tile: nothing but descriptor adds between the UTCHMMAs
+        B2O_TIMED_WAIT(dbg_a, mbar_wait(&a_full[sa], pa))
         tcgen05_after_sync();
-        const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
         if (elect_one()) {
           uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa * p.group) * a_step);
           uint32_t accumulate = 0;
@@ -404,85 +429,61 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         __syncwarp();
         if (++sa == p.na) { sa = 0; pa ^= 1; }
         if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        continue;
       }
-    } else
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      B2O_TIMED_WAIT(dbg_t, mbar_wait(&tmem_empty[acc], acc_phase ^ 1))
-#ifdef B2O_TC_DEBUG
-      ++dbg_tiles;
-#endif
       tcgen05_after_sync();
-      const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
-      const bool zero_owner = (static_cast<int>(q % static_cast<uint32_t>(p.issuers)) == me);
-      bool need_order = !zero_owner, first = true, issued = false;
       for (int g = 0; g < groups; ++g) {
         for (int kc = 0; kc < kchunks; ++kc) {
-          if (static_cast<int>(q % static_cast<uint32_t>(p.issuers)) == me) {
-            B2O_TIMED_WAIT(dbg_a, mbar_wait(&a_full[sa], pa))
-            if (need_order) { mbar_wait(&order_bar[acc], acc_phase); need_order = false; }
-            const uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa) * a_step);
-            const bool zeroing = first && zero_owner;      // this stage holds the tile's accumulator-zeroing MMA
-            if (RESIDENT || TAPS_PER_A == 1) {
-              // ONE elected region per stage: all taps' MMAs back to back, then the commits (every scalar
-              // instruction between two UTCHMMAs is exposed because the pipe has no queue to speak of)
-              uint64_t bdesc[TAPS_PER_A];
+          B2O_TIMED_WAIT(dbg_a, mbar_wait(&a_full[sa], pa))
+          const uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa) * a_step);
+          const bool zeroing = g == 0 && kc == 0;          // this stage holds the tile's accumulator-zeroing MMA
+          if (RESIDENT || TAPS_PER_A == 1) {
+            // ONE elected region per stage: all taps' MMAs back to back, then the commits
+            uint64_t bdesc[TAPS_PER_A];
 #pragma unroll
-              for (int t = 0; t < TAPS_PER_A; ++t)
-                bdesc[t] = b_desc0 + static_cast<uint64_t>(
-                               static_cast<uint32_t>(RESIDENT ? ((t * 3 + g) * kchunks + kc) : sb) * B_DESC);
-              if (!RESIDENT) B2O_TIMED_WAIT(dbg_b, mbar_wait(&b_full[sb], pb))
-              tcgen05_after_sync();
-              if (elect_one()) {
-#pragma unroll
-                for (int t = 0; t < TAPS_PER_A; ++t) {
-#pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k)
-                    // dy tap t = the stage shifted by t rows of 8 pixels; k-step = +32 B inside the swizzle atom
-                    umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc[t] + static_cast<uint64_t>(2 * k),
-                             idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
-                }
-                if (!RESIDENT) umma_commit(&b_empty[sb]);
-                umma_commit(&a_empty[sa]);                 // frees the A slot when this warp's MMAs retire
-                if (zeroing) mbar_arrive(&order_bar[acc]); // the zeroing MMA is in the pipe
-              }
-            } else {
-              // halo tiles with a streamed filter bank: one B slot per dy tap, waited for tap by tap
-              int sbl = sb;
-              uint32_t pbl = pb;
-              tcgen05_after_sync();
+            for (int t = 0; t < TAPS_PER_A; ++t)
+              bdesc[t] = b_desc0 + static_cast<uint64_t>(
+                             static_cast<uint32_t>(RESIDENT ? ((t * 3 + g) * kchunks + kc) : sb) * B_DESC);
+            if (!RESIDENT) B2O_TIMED_WAIT(dbg_b, mbar_wait(&b_full[sb], pb))
+            tcgen05_after_sync();
+            if (elect_one()) {
 #pragma unroll
               for (int t = 0; t < TAPS_PER_A; ++t) {
-                B2O_TIMED_WAIT(dbg_b, mbar_wait(&b_full[sbl], pbl))
-                tcgen05_after_sync();
-                const uint64_t bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sbl) * B_DESC);
-                if (elect_one()) {
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k)
-                    umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k),
-                             idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
-                  umma_commit(&b_empty[sbl]);
-                  if (t == TAPS_PER_A - 1) umma_commit(&a_empty[sa]);
-                  if (t == 0 && zeroing) mbar_arrive(&order_bar[acc]);
-                }
-                __syncwarp();
-                if (++sbl == p.nb) { sbl = 0; pbl ^= 1; }
+                for (int k = 0; k < KSTEPS; ++k)
+                  // dy tap t = the stage shifted by t rows of 8 pixels; k-step = +32 B inside the swizzle atom
+                  umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc[t] + static_cast<uint64_t>(2 * k),
+                           idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
               }
+              if (!RESIDENT) umma_commit(&b_empty[sb]);
+              umma_commit(&a_empty[sa]);                   // frees the A slot when these MMAs retire
             }
             __syncwarp();
-            issued = true;
-          }
-          first = false;
-          ++q;
-          if (++sa == p.na) { sa = 0; pa ^= 1; }
-          if (!RESIDENT) {
+            if (!RESIDENT) { if (++sb == p.nb) { sb = 0; pb ^= 1; } }
+          } else {
+            // halo tiles with a streamed filter bank: one B slot per dy tap, waited for tap by tap
+            tcgen05_after_sync();
 #pragma unroll
-            for (int t = 0; t < TAPS_PER_A; ++t) { if (++sb == p.nb) { sb = 0; pb ^= 1; } }
+            for (int t = 0; t < TAPS_PER_A; ++t) {
+              B2O_TIMED_WAIT(dbg_b, mbar_wait(&b_full[sb], pb))
+              tcgen05_after_sync();
+              const uint64_t bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sb) * B_DESC);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k)
+                  umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                           idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
+                umma_commit(&b_empty[sb]);
+                if (t == TAPS_PER_A - 1) umma_commit(&a_empty[sa]);
+              }
+              __syncwarp();
+              if (++sb == p.nb) { sb = 0; pb ^= 1; }
+            }
           }
+          if (++sa == p.na) { sa = 0; pa ^= 1; }
         }
       }
-      if (elect_one()) {
-        if (issued) umma_commit(&tmem_full[acc]); else mbar_arrive(&tmem_full[acc]);
-      }
+      if (elect_one()) umma_commit(&tmem_full[acc]);
       __syncwarp();
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
@@ -759,7 +760,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   p.total_tiles = static_cast<int>(total);
 
   // shared-memory plan: [A ring][B ring | resident filter bank][barriers]
-  p.issuers = ctx->tc_issuers;
+  p.issuers = 1;
   const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/;
   p.a_bytes = p.halo ? 18 * 8 * kch * 2 : 128 * kch * 2;
   p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
@@ -768,10 +769,14 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   if (p.resident) {
     p.na = static_cast<int>((budget - res_bytes) / p.a_stride);
     const int n_a = 3 * kchunks;                           // A stages per tile
-    if (p.issuers == 1 && p.na >= 2 * n_a) {               // MODE 3: whole tiles per barrier
+    if (p.na >= 2 * n_a) {                                 // MODE 3: whole tiles per barrier
       p.group = n_a;
       p.na = p.na / n_a;
       if (p.na > MAX_RING) p.na = MAX_RING;
+      if (bn <= 128 && ctx->tc_issuers != 1) {             // two issuers on alternate tiles: even rings (see top)
+        p.na &= ~1;
+        p.issuers = 2;
+      }
       p.off_b = p.na * n_a * p.a_stride;
     } else {
       if (p.na > MAX_RING) p.na = MAX_RING;
