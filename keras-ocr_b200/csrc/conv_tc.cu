@@ -204,9 +204,11 @@ struct TileIter {
   int d0, d1, d2, d3;        // gridDim.x in the same radix
   int r0, r1, r2;            // radices: n_tiles, tiles_w, tiles_h
   int tile, step, total;
-  __device__ __forceinline__ TileIter(const TcParams& p) {
+  // the CTA's tiles are blockIdx.x + i * gridDim.x; this iterator visits i = first, first + mult, ...
+  __device__ __forceinline__ TileIter(const TcParams& p, int first = 0, int mult = 1) {
     r0 = p.n_tiles; r1 = p.tiles_w; r2 = p.tiles_h;
-    total = p.total_tiles; step = static_cast<int>(gridDim.x); tile = static_cast<int>(blockIdx.x);
+    total = p.total_tiles; step = static_cast<int>(gridDim.x) * mult;
+    tile = static_cast<int>(blockIdx.x) + first * static_cast<int>(gridDim.x);
     int t = tile;
     c0 = t % r0; t /= r0; c1 = t % r1; t /= r1; c2 = t % r2; c3 = t / r2;
     t = step;
@@ -223,6 +225,48 @@ struct TileIter {
 };
 
 // ------------------------------------------------------------------------------------------ kernel
+// Epilogue arithmetic of one 16-column accumulator chunk: y = relu?(acc * s1 + t1) [* s2 + t2].
+__device__ __forceinline__ void epi_affine(const TcParams& p, const uint32_t* v, int c0, float* y) {
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p.s1 + c0 + j));
+    const float4 b = __ldg(reinterpret_cast<const float4*>(p.t1 + c0 + j));
+    y[j + 0] = fmaf(__uint_as_float(v[j + 0]), a.x, b.x);
+    y[j + 1] = fmaf(__uint_as_float(v[j + 1]), a.y, b.y);
+    y[j + 2] = fmaf(__uint_as_float(v[j + 2]), a.z, b.z);
+    y[j + 3] = fmaf(__uint_as_float(v[j + 3]), a.w, b.w);
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.0f);
+  }
+  if (p.s2 != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p.s2 + c0 + j));
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.t2 + c0 + j));
+      y[j + 0] = fmaf(y[j + 0], a.x, b.x);
+      y[j + 1] = fmaf(y[j + 1], a.y, b.y);
+      y[j + 2] = fmaf(y[j + 2], a.z, b.z);
+      y[j + 3] = fmaf(y[j + 3], a.w, b.w);
+    }
+  }
+}
+
+// 2x2/2 max pool of packed fp16 pairs across the halo tile's lanes (lane^1 = w neighbour, lane^8 = h neighbour).
+__device__ __forceinline__ void epi_pool8(uint32_t* pk) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    __half2 m = *reinterpret_cast<__half2*>(&pk[j]);
+    uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[j], 1);
+    m = __hmax2(m, *reinterpret_cast<__half2*>(&o1));
+    uint32_t mm = *reinterpret_cast<uint32_t*>(&m);
+    uint32_t o2 = __shfl_xor_sync(0xffffffffu, mm, 8);
+    m = __hmax2(m, *reinterpret_cast<__half2*>(&o2));
+    pk[j] = *reinterpret_cast<uint32_t*>(&m);
+  }
+}
+
 // MODE: 0 = generic tiles, 1 = halo tiles (3x3, dilation 1), 2 = halo tiles + resident filter bank,
 //       3 = as 2 with all A stages of a tile on ONE mbarrier (one wait + one issue region per tile)
 template <int BLOCK_N, int KCH, int MODE>
@@ -505,14 +549,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     const int wi = row & bw_mask;
     const int hi = (row >> p.bw_log2) & bh_mask;
     const int ni = row >> (p.bw_log2 + p.bh_log2);
-    int acc = 0;
+    // TILE_PAR: this warp owns tiles sub, sub + 4, ... of the CTA (and their accumulator stages)
+    constexpr int ACC_STEP = TILE_PAR ? 4 : 1;
+    int acc = TILE_PAR ? (sub % ACC_STAGES) : 0;
     uint32_t acc_phase = 0;
-    int tile_seq = 0;
-    for (TileIter ti(p); ti.valid(); ti.next(), ++tile_seq) {
-      if (TILE_PAR && (tile_seq & 3) != sub) {             // another warp of this quadrant owns the tile
-        if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
-        continue;
-      }
+    for (TileIter ti(p, TILE_PAR ? sub : 0, ACC_STEP); ti.valid(); ti.next()) {
       const int w = (ti.c1 << p.bw_log2) + wi, h = (ti.c2 << p.bh_log2) + hi, n = (ti.c3 << p.bn_log2) + ni;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
@@ -532,30 +573,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         tmem_ld_wait();
         const int c0 = c_base + ch * CH;
         float y[CH];
-#pragma unroll
-        for (int j = 0; j < CH; j += 4) {
-          const float4 a = __ldg(reinterpret_cast<const float4*>(p.s1 + c0 + j));
-          const float4 b = __ldg(reinterpret_cast<const float4*>(p.t1 + c0 + j));
-          y[j + 0] = fmaf(__uint_as_float(v[j + 0]), a.x, b.x);
-          y[j + 1] = fmaf(__uint_as_float(v[j + 1]), a.y, b.y);
-          y[j + 2] = fmaf(__uint_as_float(v[j + 2]), a.z, b.z);
-          y[j + 3] = fmaf(__uint_as_float(v[j + 3]), a.w, b.w);
-        }
-        if (p.relu) {
-#pragma unroll
-          for (int j = 0; j < CH; ++j) y[j] = fmaxf(y[j], 0.0f);
-        }
-        if (p.s2 != nullptr) {
-#pragma unroll
-          for (int j = 0; j < CH; j += 4) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p.s2 + c0 + j));
-            const float4 b = __ldg(reinterpret_cast<const float4*>(p.t2 + c0 + j));
-            y[j + 0] = fmaf(y[j + 0], a.x, b.x);
-            y[j + 1] = fmaf(y[j + 1], a.y, b.y);
-            y[j + 2] = fmaf(y[j + 2], a.z, b.z);
-            y[j + 3] = fmaf(y[j + 3], a.w, b.w);
-          }
-        }
+        epi_affine(p, v, c0, y);
         if (p.out_f32) {
           if (valid) {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + c0;
@@ -586,16 +604,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             }
           }
           if (p.pool_out != nullptr) {                    // warp-uniform branch
-#pragma unroll
-            for (int j = 0; j < CH / 2; ++j) {
-              __half2 m = *reinterpret_cast<__half2*>(&pk[j]);
-              uint32_t o1 = __shfl_xor_sync(0xffffffffu, pk[j], 1);
-              m = __hmax2(m, *reinterpret_cast<__half2*>(&o1));
-              uint32_t mm = *reinterpret_cast<uint32_t*>(&m);
-              uint32_t o2 = __shfl_xor_sync(0xffffffffu, mm, 8);
-              m = __hmax2(m, *reinterpret_cast<__half2*>(&o2));
-              pk[j] = *reinterpret_cast<uint32_t*>(&m);
-            }
+            epi_pool8(pk);
             if (pool_writer) {
               __half* o = p.pool_out + ppix * p.pool_ld + c0;
               if (p.wide) {
@@ -611,7 +620,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       }
       tcgen05_before_sync();
       mbar_arrive(&tmem_empty[acc]);                       // TMEM stage drained: the MMA warps may reuse it
-      if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      acc += ACC_STEP;
+      if (acc >= ACC_STAGES) { acc -= ACC_STAGES; acc_phase ^= 1; }
     }
   }
 
