@@ -330,7 +330,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&tmem_full[s], 1);                          // the commit of the warp that issued the tile
-      mbar_init(&tmem_empty[s], TILE_PAR ? 128 : EPI_THREADS);
+      mbar_init(&tmem_empty[s], TILE_PAR ? 4 : EPI_THREADS / 32);   // one arrival per epilogue warp on the tile
       mbar_init(&order_bar[s], 1);
     }
     mbar_init(res_full, 1);
@@ -581,11 +581,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
-#pragma unroll 1
-      for (int ch = TILE_PAR ? 0 : sub; ch < BLOCK_N / CH; ch += TILE_PAR ? 1 : 4) {
-        uint32_t v[CH];
-        tmem_ld<CH>(taddr + static_cast<uint32_t>(ch * CH), v);
-        tmem_ld_wait();
+      // one 16-column chunk: affine/ReLU -> stores (+ fused pool)
+      auto chunk = [&](const uint32_t* v, const int ch) {
         const int c0 = c_base + ch * CH;
         float y[CH];
         epi_affine(p, e_s1, e_t1, e_s2, e_t2, v, c0, y);
@@ -632,9 +629,31 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             }
           }
         }
+      };
+      // chunks two at a time: both TMEM loads are in flight before the single wait
+      constexpr int CH_FIRST_STEP = TILE_PAR ? 1 : 4;
+      constexpr int PER_WARP = TILE_PAR ? BLOCK_N / CH : BLOCK_N / CH / 4;
+      const int ch_first = TILE_PAR ? 0 : sub;
+      if (PER_WARP >= 2) {
+#pragma unroll 1
+        for (int i = 0; i < PER_WARP; i += 2) {
+          const int cha = ch_first + i * CH_FIRST_STEP, chb = cha + CH_FIRST_STEP;
+          uint32_t va[CH], vb[CH];
+          tmem_ld<CH>(taddr + static_cast<uint32_t>(cha * CH), va);
+          tmem_ld<CH>(taddr + static_cast<uint32_t>(chb * CH), vb);
+          tmem_ld_wait();
+          chunk(va, cha);
+          chunk(vb, chb);
+        }
+      } else {
+        uint32_t va[CH];
+        tmem_ld<CH>(taddr + static_cast<uint32_t>(ch_first * CH), va);
+        tmem_ld_wait();
+        chunk(va, ch_first);
       }
       tcgen05_before_sync();
-      mbar_arrive(&tmem_empty[acc]);                       // TMEM stage drained: the MMA warps may reuse it
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // TMEM stage drained (one arrival per warp)
       acc += ACC_STEP;
       if (acc >= ACC_STAGES) { acc -= ACC_STAGES; acc_phase ^= 1; }
     }
