@@ -36,8 +36,9 @@ class Recognizer:
             checkpoint's ``fc_12`` must have ``len(alphabet) + 1`` classes; if it does not, the reference's
             "backbone weights only" behaviour applies (recognition.py:399-411): the top layer is
             re-initialised (Glorot uniform, zero bias) and has to be trained before it is useful.
-        weights: ``"kurapan"`` needs a converted ``crnn_kurapan.npz`` in the cache dir (Keras ``.h5``
-            cannot be read without h5py); otherwise a ``.npz`` path or a dict keyed like ``weights.py``.
+        weights: ``"kurapan"`` looks for ``crnn_kurapan.npz`` (exported) or the reference's ``crnn_kurapan.h5``
+            (read with h5py where installed) in the cache dir; otherwise a ``.npz`` / ``.h5`` path or a dict
+            keyed like ``weights.py``.
         build_params: must be ``None`` / the defaults (reference recognition.py:13-23).
     """
 
@@ -57,8 +58,16 @@ class Recognizer:
             tensors = weights
         elif isinstance(weights, str) and weights.endswith(".npz"):
             tensors = weights_mod.load_npz(weights)
-        elif weights == "kurapan":
-            tensors = weights_mod.load_npz(tools.find_cached("crnn_kurapan.npz"))
+        elif isinstance(weights, str) and weights.endswith(".h5"):
+            tensors = weights_mod.load_keras_h5(weights)
+        elif weights == "kurapan":                                # recognition.py:27-44: cache file, sha256-verified
+            import os
+            cache = tools.get_default_cache_dir()
+            if os.path.isfile(os.path.join(cache, "crnn_kurapan.npz")):
+                tensors = weights_mod.load_npz(os.path.join(cache, "crnn_kurapan.npz"))
+            else:
+                tensors = weights_mod.load_keras_h5(tools.find_cached(
+                    "crnn_kurapan.h5", sha256="a7d8086ac8f5c3d6a0a828f7d6fbabcaf815415dd125c32533013f85603be46d"))
         else:
             raise NotImplementedError(f"Cannot load weights from {weights}")
         n_classes = len(self.alphabet) + 1

@@ -195,3 +195,52 @@ def load_npz(path):
     """Weights exported to a flat ``.npz`` with the key names documented above."""
     with np.load(path) as data:
         return {k: data[k].astype(np.float32) for k in data.files}
+
+
+# --------------------------------------------------------------------------------------- Keras HDF5
+_CRNN_NAMED = ({f"conv_{i}" for i in range(1, 8)} | {"bn_3", "bn_5", "bn_7", "fc_9", "fc_12"} | set(CRNN_LSTMS))
+_KINDS = ("kernel", "recurrent_kernel", "bias", "gamma", "beta", "moving_mean", "moving_variance")
+_STN_BY_SHAPE = {(5, 5, 512, 16): "stn.conv_a.kernel", (5, 5, 16, 32): "stn.conv_b.kernel",
+                 (11200, 64): "stn.dense_a.kernel", (64, 6): "stn.dense_b.kernel",
+                 (16,): "stn.conv_a.bias", (32,): "stn.conv_b.bias", (64,): "stn.dense_a.bias", (6,): "stn.dense_b.bias"}
+
+
+def map_keras_datasets(flat):
+    """Keras (TF2 ``save_weights`` HDF5) dataset paths -> the keys of this module.
+
+    ``flat`` maps a dataset path such as ``conv_3/conv_3/kernel:0`` or ``lstm_10/lstm_10/lstm_cell/bias:0`` to its
+    array.  Named layers of ``build_model`` (reference recognition.py:214-329) map by name; the nested localisation
+    model of the spatial transformer is auto-named by Keras (``model_N/conv2d_M/...``, recognition.py:263-277), so its
+    eight tensors are told apart by their shapes, which are all distinct."""
+    out = {}
+    for path, arr in flat.items():
+        parts = [q for q in path.split("/") if q]
+        kind = parts[-1].split(":")[0]
+        if kind not in _KINDS:
+            continue
+        arr = np.asarray(arr, dtype=np.float32)
+        if parts[0] in _CRNN_NAMED:
+            key = f"{parts[0]}.{kind}"
+        else:
+            key = _STN_BY_SHAPE.get(tuple(arr.shape))
+            if key is None or not key.endswith(kind):
+                raise ValueError(f"unrecognised tensor {path} with shape {arr.shape} in Keras weight file")
+        if key in out:
+            raise ValueError(f"two tensors map to {key} (second: {path})")
+        out[key] = arr
+    return out
+
+
+def load_keras_h5(path):
+    """Read the reference's ``crnn_kurapan.h5`` / ``crnn_kurapan_notop.h5`` (recognition.py:27-44).  Needs h5py,
+    which this offline image does not have: export to ``.npz`` once where it is available."""
+    try:
+        import h5py
+    except ImportError as exc:
+        raise ImportError("reading Keras .h5 weights needs h5py; export them to .npz once with "
+                          "keras_ocr_b200.weights.load_keras_h5 + numpy.savez on a machine that has it") from exc
+    flat = {}
+    with h5py.File(path, "r") as f:
+        root = f["model_weights"] if "model_weights" in f else f
+        root.visititems(lambda name, obj: flat.__setitem__(name, np.array(obj)) if isinstance(obj, h5py.Dataset) else None)
+    return map_keras_datasets(flat)

@@ -55,3 +55,32 @@ def test_adjust_boxes_and_read_contracts(tmp_path):
     cv2.imwrite(path, img[..., ::-1])
     assert np.array_equal(tools.read(path), img)             # BGR file -> RGB array
     assert tools.read(img) is img
+
+
+def test_keras_h5_dataset_mapping_round_trip():
+    """weights.map_keras_datasets: Keras save_weights paths (named layers by name, the auto-named localisation
+    model by shape) -> this package's keys; round trip of a full synthetic CRNN checkpoint."""
+    from keras_ocr_b200 import weights as W
+    w = W.synthetic_crnn_weights(4)
+    flat = {}
+    stn_names = {"stn.conv_a": "model_1/conv2d_8", "stn.conv_b": "model_1/conv2d_9",
+                 "stn.dense_a": "model_1/dense_3", "stn.dense_b": "model_1/dense_4"}
+    for key, arr in w.items():
+        layer, kind = key.rsplit(".", 1)
+        if layer in stn_names:
+            flat[f"{stn_names[layer]}/{kind}:0"] = arr
+        elif layer.startswith("lstm"):
+            flat[f"{layer}/{layer}/lstm_cell_7/{kind}:0"] = arr
+        else:
+            flat[f"{layer}/{layer}/{kind}:0"] = arr
+    flat["optimizer_weights/iter:0"] = np.zeros(())           # ignored
+    back = W.map_keras_datasets(flat)
+    assert set(back) == set(w)
+    assert all(np.array_equal(back[k], w[k]) for k in w)
+    with pytest.raises(ValueError):
+        W.map_keras_datasets({"model_1/conv2d_8/kernel:0": np.zeros((3, 3, 8, 8), np.float32)})
+    try:
+        import h5py  # noqa: F401
+    except ImportError:
+        with pytest.raises(ImportError):
+            W.load_keras_h5("/nonexistent/crnn_kurapan.h5")
