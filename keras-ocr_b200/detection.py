@@ -84,28 +84,50 @@ class Detector:
         self.ctx.craft_forward(images_t.data_ptr(), n, h, w, scores.data_ptr(), ws.data_ptr(), nbytes, stream)
         return scores
 
+    def boxes_enqueue(self, scores, detection_threshold=0.7, text_threshold=0.4, link_threshold=0.4,
+                      size_threshold=10):
+        """getBoxes on the device, asynchronously: launches the kernels and the copy of the per-image counts into
+        pinned memory, records an event and returns at once (``boxes_finish`` waits for that event only, so work
+        enqueued afterwards keeps the GPU busy while the host reads the counts)."""
+        n, hs, ws_, _ = scores.shape
+        stream = torch.cuda.current_stream(self.device)
+        scores = scores.contiguous()
+        m = self.max_boxes
+        boxes = torch.empty((n, m, 4, 2), dtype=torch.float32, device=self.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=self.device)
+        nbytes = self.ctx.boxes_workspace_bytes(n, hs, ws_, m)
+        if self._box_ws is None or self._box_ws.numel() < nbytes:
+            self._box_ws = None
+            self._box_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        wsp = self._box_ws
+        thr = (float(detection_threshold), float(text_threshold), float(link_threshold), int(size_threshold))
+        self.ctx.get_boxes(scores.data_ptr(), n, hs, ws_, *thr, boxes.data_ptr(), counts.data_ptr(), m,
+                           wsp.data_ptr(), nbytes, stream.cuda_stream)
+        counts_pin = torch.empty((n,), dtype=torch.int32, pin_memory=True)
+        counts_pin.copy_(counts, non_blocking=True)
+        event = torch.cuda.Event()
+        event.record(stream)
+        return {"scores": scores, "boxes": boxes, "counts_pin": counts_pin, "event": event, "m": m, "thr": thr}
+
+    def boxes_finish(self, state):
+        """Wait for ``boxes_enqueue``.  Returns (boxes (N,M,4,2) float32 CUDA, counts ndarray (N,)); re-runs
+        getBoxes with a larger box table in the (rare) case an image had more boxes than the table holds."""
+        state["event"].synchronize()                     # the one synchronisation of the detector half
+        counts_host = state["counts_pin"].numpy().copy()
+        boxes = state["boxes"]
+        while counts_host.size and int(counts_host.max()) > boxes.shape[1]:
+            self.max_boxes = int(2 ** np.ceil(np.log2(int(counts_host.max()))))
+            d, t, l, s = state["thr"]
+            again = self.boxes_enqueue(state["scores"], d, t, l, s)
+            again["event"].synchronize()
+            counts_host, boxes = again["counts_pin"].numpy().copy(), again["boxes"]
+        return boxes, counts_host
+
     def boxes_device(self, scores, detection_threshold=0.7, text_threshold=0.4, link_threshold=0.4,
                      size_threshold=10):
         """getBoxes on the device.  Returns (boxes (N,M,4,2) float32 CUDA, counts ndarray (N,))."""
-        n, hs, ws_, _ = scores.shape
-        stream = torch.cuda.current_stream(self.device).cuda_stream
-        scores = scores.contiguous()
-        while True:
-            m = self.max_boxes
-            boxes = torch.empty((n, m, 4, 2), dtype=torch.float32, device=self.device)
-            counts = torch.empty((n,), dtype=torch.int32, device=self.device)
-            nbytes = self.ctx.boxes_workspace_bytes(n, hs, ws_, m)
-            if self._box_ws is None or self._box_ws.numel() < nbytes:
-                self._box_ws = None
-                self._box_ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
-            wsp = self._box_ws
-            self.ctx.get_boxes(scores.data_ptr(), n, hs, ws_, float(detection_threshold), float(text_threshold),
-                               float(link_threshold), int(size_threshold), boxes.data_ptr(), counts.data_ptr(), m,
-                               wsp.data_ptr(), nbytes, stream)
-            counts_host = counts.cpu().numpy()          # the one synchronisation of the detector half
-            if counts_host.size == 0 or int(counts_host.max()) <= m:
-                return boxes, counts_host
-            self.max_boxes = int(2 ** np.ceil(np.log2(int(counts_host.max()))))
+        return self.boxes_finish(self.boxes_enqueue(scores, detection_threshold, text_threshold, link_threshold,
+                                                    size_threshold))
 
     def detect_device(self, images_t, **thresholds):
         return self.boxes_device(self.predict_device(images_t), **thresholds)

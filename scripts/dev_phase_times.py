@@ -34,8 +34,16 @@ for rep in range(3):
     t.append(T())
     names = ["prepare", "craft", "get_boxes", "warp+crnn", "d2h", "strings", "assemble"]
     print(" ".join(f"{n}={1e3*(b-a):.2f}ms" for n, a, b in zip(names, t, t[1:])), f"total={1e3*(t[-1]-t[0]):.2f}ms")
-t0 = T()
-for _ in range(5):
+for inflight in (1, 2, 1, 2):
+    pipe.inflight = inflight
     pipe.recognize(dev)
-t1 = T()
-print(f"recognize(): {(t1-t0)/5*1e3:.2f} ms/step")
+    t0 = T()
+    for _ in range(5):
+        pipe.recognize(dev)
+    t1 = T()
+    pipe.recognize(pages)
+    t2 = T()
+    for _ in range(5):
+        pipe.recognize(pages)
+    t3 = T()
+    print(f"inflight={inflight}: recognize(device) {(t1-t0)/5*1e3:.2f} ms/step, recognize(numpy) {(t3-t2)/5*1e3:.2f} ms/step")
