@@ -80,60 +80,93 @@ __global__ void stn_sample_kernel(const __half* __restrict__ feat, const float* 
 // ---------------------------------------------------------------------------------------- LSTM
 constexpr int kUnits = 128, kGates = 512, kSteps = 50;
 constexpr int kCropsPerCta = 8;
+constexpr int kHPitch = kUnits + 8;      // halves per crop row of h: +16 B so the 8 crops hit different banks
 
 __device__ __forceinline__ float sigmoidf_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
 
+__device__ __forceinline__ void mma_m16n8k16(float* d, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// One CTA = 8 crops, 16 warps, 50 strictly sequential steps, so what matters is the latency of one step.  The
+// recurrent product z[512 gates x 8 crops] = U^T[512 x 128] . h^T[128 x 8] is exactly the m16n8k16 warp MMA
+// shape with the crops as N: warp w owns units 8w..8w+7 and keeps its two 16-row slices of U^T
+// ({i,f} gates and {c,o} gates of those units, all 128 k) in registers for the whole sequence; the D fragment
+// then hands every thread all four gates of one unit for two crops, so the gate arithmetic needs no exchange
+// and the only shared data is the fp16 h vector (double-buffered, one __syncthreads per step).  tcgen05 does
+// not apply: M = 128 rows would be 94 % padding and its issue -> commit -> tcgen05.ld round trip is longer
+// than this whole step.  h is rounded to fp16 between steps -- the same value that is written to `out`.
 // xw  : (B*T, xw_ld) fp32 input projections x@W + b; this direction's 512 gate columns start at xw_off
-// u   : (128, 512) fp16 recurrent kernel (row k = previous-h unit, column g = gate)
+// u   : (128, 512) fp16 recurrent kernel (row k = previous-h unit, column g = gate; Keras order i,f,c,o)
 // out : (B, T, out_ld) fp16, written at channel offset out_off, indexed by PROCESSING step
 __global__ void __launch_bounds__(kGates, 1)
 lstm_kernel(const float* __restrict__ xw, int xw_ld, int xw_off, const __half* __restrict__ u, int B, int backwards,
             __half* __restrict__ out, int out_ld, int out_off) {
-  __shared__ __align__(16) float h_s[kCropsPerCta][kUnits];
-  __shared__ float z_s[kCropsPerCta][kGates];
-  const int g = threadIdx.x;
+  __shared__ __align__(16) __half h_s[2][kCropsPerCta][kHPitch];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = lane >> 2, q = lane & 3;
+  const int unit = warp * 8 + r;                         // this thread's unit (all four gates)
+  const int cA = q * 2;                                  // this thread's crops: cA, cA + 1
   const int b0 = blockIdx.x * kCropsPerCta;
   const int nb = min(kCropsPerCta, B - b0);
-  // this thread's column of U, as (k, k+1) pairs
-  __half2 ucol[kUnits / 2];
+
+  // A fragments of U^T: tile 0 rows = {i[unit], f[unit]}, tile 1 rows = {c[unit], o[unit]}
+  uint32_t afrag[2][kUnits / 16][4];
 #pragma unroll
-  for (int k = 0; k < kUnits / 2; ++k)
-    ucol[k] = __halves2half2(u[(2 * k) * kGates + g], u[(2 * k + 1) * kGates + g]);
-  for (int i = threadIdx.x; i < kCropsPerCta * kUnits; i += blockDim.x) (&h_s[0][0])[i] = 0.0f;
-  float c_state[2] = {0.0f, 0.0f};        // cell state of work items (g) and (g + 512) in the gate phase
+  for (int tile = 0; tile < 2; ++tile)
+#pragma unroll
+    for (int kt = 0; kt < kUnits / 16; ++kt) {
+      const int col_lo = (2 * tile) * kUnits + unit, col_hi = (2 * tile + 1) * kUnits + unit;
+      const int k0 = kt * 16 + q * 2;
+      auto pack = [&](int k, int col) {
+        const __half2 v = __halves2half2(u[k * kGates + col], u[(k + 1) * kGates + col]);
+        return *reinterpret_cast<const uint32_t*>(&v);
+      };
+      afrag[tile][kt][0] = pack(k0, col_lo);
+      afrag[tile][kt][1] = pack(k0, col_hi);
+      afrag[tile][kt][2] = pack(k0 + 8, col_lo);
+      afrag[tile][kt][3] = pack(k0 + 8, col_hi);
+    }
+  for (int i = threadIdx.x; i < 2 * kCropsPerCta * kHPitch; i += blockDim.x) (&h_s[0][0][0])[i] = __float2half_rn(0.0f);
+
+  // input projections of (crop cA / cA+1) x (gates i,f,c,o of `unit`), prefetched one step ahead
+  const bool okA = cA < nb, okB = cA + 1 < nb;
+  auto load_x = [&](int t, float* z) {
+    const float* pa = xw + (static_cast<size_t>(b0 + cA) * kSteps + t) * xw_ld + xw_off + unit;
+    const float* pb = pa + static_cast<size_t>(kSteps) * xw_ld;
+#pragma unroll
+    for (int gidx = 0; gidx < 4; ++gidx) {
+      z[2 * gidx] = okA ? pa[gidx * kUnits] : 0.0f;
+      z[2 * gidx + 1] = okB ? pb[gidx * kUnits] : 0.0f;
+    }
+  };
+  float xnext[8];
+  load_x(backwards ? kSteps - 1 : 0, xnext);
+  float c_state[2] = {0.0f, 0.0f};
   __syncthreads();
   for (int step = 0; step < kSteps; ++step) {
-    const int t = backwards ? (kSteps - 1 - step) : step;
-    float acc[kCropsPerCta];
+    // D fragments: d0 = {i[cA], i[cB], f[cA], f[cB]}, d1 = {c[cA], c[cB], o[cA], o[cB]}
+    float d0[4] = {xnext[0], xnext[1], xnext[2], xnext[3]};
+    float d1[4] = {xnext[4], xnext[5], xnext[6], xnext[7]};
+    if (step + 1 < kSteps) load_x(backwards ? (kSteps - 2 - step) : (step + 1), xnext);
+    const __half* hrow = &h_s[step & 1][r][q * 2];     // B fragment: h[crop r][k0 .. k0+1], [k0+8 .. k0+9]
 #pragma unroll
-    for (int b = 0; b < kCropsPerCta; ++b)
-      acc[b] = (b < nb) ? xw[(static_cast<size_t>(b0 + b) * kSteps + t) * xw_ld + xw_off + g] : 0.0f;
-#pragma unroll
-    for (int k = 0; k < kUnits / 2; ++k) {
-      const float2 uk = __half22float2(ucol[k]);
-#pragma unroll
-      for (int b = 0; b < kCropsPerCta; ++b) {
-        const float2 hv = *reinterpret_cast<const float2*>(&h_s[b][2 * k]);
-        acc[b] = fmaf(hv.x, uk.x, acc[b]);
-        acc[b] = fmaf(hv.y, uk.y, acc[b]);
-      }
+    for (int kt = 0; kt < kUnits / 16; ++kt) {
+      const uint32_t b0r = *reinterpret_cast<const uint32_t*>(hrow + kt * 16);
+      const uint32_t b1r = *reinterpret_cast<const uint32_t*>(hrow + kt * 16 + 8);
+      mma_m16n8k16(d0, afrag[0][kt], b0r, b1r);
+      mma_m16n8k16(d1, afrag[1][kt], b0r, b1r);
     }
 #pragma unroll
-    for (int b = 0; b < kCropsPerCta; ++b) z_s[b][g] = acc[b];
-    __syncthreads();
-    // gate phase: 8 crops x 128 units = 1024 items over 512 threads
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const int item = g + r * kGates;
-      const int b = item / kUnits, j = item - b * kUnits;
-      if (b < nb) {
-        const float zi = z_s[b][j], zf = z_s[b][kUnits + j], zc = z_s[b][2 * kUnits + j], zo = z_s[b][3 * kUnits + j];
-        const float c = sigmoidf_acc(zf) * c_state[r] + sigmoidf_acc(zi) * tanhf(zc);
-        const float h = sigmoidf_acc(zo) * tanhf(c);
-        c_state[r] = c;
-        h_s[b][j] = h;
-        out[(static_cast<size_t>(b0 + b) * kSteps + step) * out_ld + out_off + j] = __float2half_rn(h);
-      }
+    for (int e = 0; e < 2; ++e) {                         // e = 0: crop cA, e = 1: crop cA + 1
+      const float zi = d0[e], zf = d0[2 + e], zc = d1[e], zo = d1[2 + e];
+      const float c = sigmoidf_acc(zf) * c_state[e] + sigmoidf_acc(zi) * tanhf(zc);
+      const __half h = __float2half_rn(sigmoidf_acc(zo) * tanhf(c));
+      c_state[e] = c;
+      h_s[(step + 1) & 1][cA + e][unit] = h;
+      if (cA + e < nb) out[(static_cast<size_t>(b0 + cA + e) * kSteps + step) * out_ld + out_off + unit] = h;
     }
     __syncthreads();
   }

@@ -433,6 +433,27 @@ def test_results_are_bit_reproducible(detector, recognizer):
         assert torch.equal(recognizer.tap("logits", (24, 48, 37), torch.float32), logits)
 
 
+def test_pipelined_sub_batches_give_identical_results(cuda_device):
+    """Pipeline(inflight=2) splits the batch into software-pipelined sub-batches; every (text, box) must equal
+    the unsplit run exactly, for same-size arrays and for ragged lists (whole-batch padding is kept)."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import synth
+    det = Detector(weights=W.synthetic_craft_weights(3, textlike=True))
+    rec = Recognizer(weights=W.synthetic_crnn_weights(2))
+    pages, _ = synth.text_images(seed=77, n=9, h=256, w=320, n_words=6)
+    ragged = [pages[i][: 256 - 16 * (i % 3), : 320 - 32 * (i % 2)] for i in range(9)]
+    for images in (pages, ragged):
+        one = Pipeline(detector=det, recognizer=rec, scale=2, inflight=1).recognize(images)
+        two = Pipeline(detector=det, recognizer=rec, scale=2, inflight=2).recognize(images)
+        assert len(one) == len(two) == 9
+        assert sum(len(g) for g in one) > 0
+        for ga, gb in zip(one, two):
+            assert [t for t, _ in ga] == [t for t, _ in gb]
+            assert all(np.array_equal(ba, bb) for (_, ba), (_, bb) in zip(ga, gb))
+
+
 def test_recognizer_single_crop_api(recognizer):
     """Recognizer.recognize(image) (recognition.py:467-489) == recognize_from_boxes on the fitted crop."""
     import cv2
