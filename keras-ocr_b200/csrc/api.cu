@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 int stn_theta_run(b2o_ctx* ctx, const __half* d1, int B, float* theta, cudaStream_t st);
+int stn_col2im_run(b2o_ctx* ctx, const __half* y, const float* bias, int B, __half* out, cudaStream_t st);
 int stn_sample_run(b2o_ctx* ctx, const __half* feat, const float* theta, int B, __half* out, cudaStream_t st);
 int lstm_run(b2o_ctx* ctx, const float* xw, int xw_ld, int xw_off, const __half* u, int B, int backwards, __half* out,
              int out_ld, int out_off, cudaStream_t st);
@@ -311,6 +312,17 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
     ConvLayer& L = ctx->crnn[s.name];
     B2O_RETURN_IF(build_layer(ctx, L, s.name, s.cin, s.cout, s.k, 1, 1, wget, s1, t1, s.bn ? &s2 : nullptr,
                               s.bn ? &t2 : nullptr, s.cin == 1));
+    if (std::string(s.name) == "stn.conv_a") {
+      // The 5x5, 512 -> 16 convolution as ONE 1x1 GEMM with N = 25 taps x 16 channels (400, padded to 512)
+      // followed by a shift-and-add of the 25 column groups (stn_col2im): 16-column MMAs cost as much tensor
+      // pipe time as 64-column ones, 256-column ones are ~5x cheaper per output.
+      auto wgemm = [wd, cin, cout, k](int o, int c, int, int) {
+        return o < k * k * cout ? wd[(static_cast<size_t>(o / cout) * cin + c) * cout + (o % cout)] : 0.0f;
+      };
+      ConvLayer& G = ctx->crnn["stn.conv_a_gemm"];
+      B2O_RETURN_IF(build_layer(ctx, G, "stn.conv_a_gemm", s.cin, 512, 1, 1, 0, wgemm, ones(512),
+                                std::vector<float>(512, 0.0f), nullptr, nullptr, false));
+    }
   }
   // dense layers as 1x1 "convolutions" over a (1,1,rows,K) view
   struct Dense { const char* name; int k, n, relu; };
@@ -489,7 +501,13 @@ extern "C" int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in, int b, int32_
   B2O_RETURN_IF(conv_run(ctx, L("conv_6"), p5, x6, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("conv_7"), x6, x7, 0, st));
   // spatial transformer (263-281)
-  B2O_RETURN_IF(conv_run(ctx, L("stn.conv_a"), x7, sa, 0, st));
+  if (ctx->conv_engine == B2O_CONV_AUTO && L("stn.conv_a_gemm").block_n != 0) {
+    const TensorView y = V(p.off_warp, b, 50, 7, 512);   // the warp buffer is free until stn_sample
+    B2O_RETURN_IF(conv_run(ctx, L("stn.conv_a_gemm"), x7, y, 0, st));
+    B2O_RETURN_IF(stn_col2im_run(ctx, y.ptr, L("stn.conv_a").t1, b, sa.ptr, st));
+  } else {
+    B2O_RETURN_IF(conv_run(ctx, L("stn.conv_a"), x7, sa, 0, st));
+  }
   B2O_RETURN_IF(conv_run(ctx, L("stn.conv_b"), sa, sb, 0, st));
   const TensorView sb_flat = make_view(base + p.off_sb, 1, 1, b, 11200), d1 = make_view(base + p.off_d1, 1, 1, b, 64);
   B2O_RETURN_IF(conv_run(ctx, L("stn.dense_a"), sb_flat, d1, 0, st));

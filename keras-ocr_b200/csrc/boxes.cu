@@ -112,26 +112,37 @@ struct Stats {        // indexed by root pixel
   int* area; int* minx; int* maxx; int* miny; int* maxy; int* maxtext;
 };
 
+// Warp-aggregated: the lanes of a warp that belong to the same component (usually one run of a word blob)
+// reduce their contribution with __reduce_*_sync over their __match_any group and the group's first lane
+// issues the six atomics -- one set per run instead of one per pixel on the same ~32 hot addresses per image.
 __global__ void stats_kernel(const float* __restrict__ scores, const int* __restrict__ label, long long total,
                              int hw, int ws, Stats st) {
   const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (p >= total) return;
-  const int r = label[p];
+  const int r = p < total ? label[p] : -1;
+  const uint32_t active = __ballot_sync(0xffffffffu, r >= 0);
   if (r < 0) return;
   const long long base = (p / hw) * hw;
   const int q = static_cast<int>(p - base);
   const int x = q % ws, y = q / ws;
   const long long ri = base + r;
-  atomicAdd(st.area + ri, 1);
-  atomicMin(st.minx + ri, x);
-  atomicMax(st.maxx + ri, x);
-  atomicMin(st.miny + ri, y);
-  atomicMax(st.maxy + ri, y);
-  atomicMax(st.maxtext + ri, float_key(scores[2 * p]));
+  const uint32_t grp = __match_any_sync(active, ri);
+  const int minx = __reduce_min_sync(grp, x), maxx = __reduce_max_sync(grp, x);
+  const int miny = __reduce_min_sync(grp, y), maxy = __reduce_max_sync(grp, y);
+  const int mt = __reduce_max_sync(grp, float_key(scores[2 * p]));
+  if ((threadIdx.x & 31) == __ffs(grp) - 1) {
+    atomicAdd(st.area + ri, __popc(grp));
+    atomicMin(st.minx + ri, minx);
+    atomicMax(st.maxx + ri, maxx);
+    atomicMin(st.miny + ri, miny);
+    atomicMax(st.maxy + ri, maxy);
+    atomicMax(st.maxtext + ri, mt);
+  }
 }
 
 // One CTA per image: walk the pixels in raster order, keep roots that pass the filters
 // (detection.py:233-241) and compact them -- the slot order is the reference's label order.
+// Each thread looks at 4 consecutive pixels per round; rounds without any kept root (almost all of them:
+// a page has tens of components in 590k pixels) cost one __syncthreads_or.
 __global__ void __launch_bounds__(1024)
 select_kernel(const int* __restrict__ label, int hw, Stats st, int size_thr, float det_thr, Component* __restrict__ comps,
               int max_boxes, int* __restrict__ counts) {
@@ -143,14 +154,28 @@ select_kernel(const int* __restrict__ label, int hw, Stats st, int size_thr, flo
   if (threadIdx.x == 0) carry = 0;
   __syncthreads();
   const int det_key = float_key(det_thr);
-  for (int start = 0; start < hw; start += blockDim.x) {
-    const int q = start + threadIdx.x;
-    int keep = 0;
-    if (q < hw && label[base + q] == q) {
-      // "size < size_threshold -> skip" and "max < detection_threshold -> skip"
-      keep = (st.area[base + q] >= size_thr) && (st.maxtext[base + q] >= det_key);
+  const bool vec = (hw % 4 == 0);                          // rows of int4 stay aligned for every image
+  for (int start = 0; start < hw; start += 4 * blockDim.x) {
+    const int q0 = start + 4 * threadIdx.x;
+    int lab[4] = {-1, -1, -1, -1};
+    if (vec && q0 + 3 < hw) {
+      const int4 v4 = *reinterpret_cast<const int4*>(label + base + q0);
+      lab[0] = v4.x; lab[1] = v4.y; lab[2] = v4.z; lab[3] = v4.w;
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (q0 + e < hw) lab[e] = label[base + q0 + e];
     }
-    int v = keep;
+    int keepmask = 0;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (lab[e] == q0 + e) {
+        // "size < size_threshold -> skip" and "max < detection_threshold -> skip"
+        if ((st.area[base + q0 + e] >= size_thr) && (st.maxtext[base + q0 + e] >= det_key)) keepmask |= 1 << e;
+      }
+    if (!__syncthreads_or(keepmask)) continue;             // block-uniform
+    const int cnt = __popc(keepmask);
+    int v = cnt;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, v, o);
@@ -159,26 +184,32 @@ select_kernel(const int* __restrict__ label, int hw, Stats st, int size_thr, flo
     if (lane == 31) warp_sums[wid] = v;
     __syncthreads();
     if (wid == 0) {
-      int s = warp_sums[lane];
+      int sacc = warp_sums[lane];
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, s, o);
-        if (lane >= o) s += t;
+        const int t = __shfl_up_sync(0xffffffffu, sacc, o);
+        if (lane >= o) sacc += t;
       }
-      warp_sums[lane] = s;
+      warp_sums[lane] = sacc;
     }
     __syncthreads();
-    const int slot = carry + (wid ? warp_sums[wid - 1] : 0) + v - keep;
-    if (keep && slot < max_boxes) {
-      Component c;
-      c.root = q;
-      c.x = st.minx[base + q];
-      c.y = st.miny[base + q];
-      c.w = st.maxx[base + q] - c.x + 1;
-      c.h = st.maxy[base + q] - c.y + 1;
-      c.area = st.area[base + q];
-      comps[static_cast<size_t>(img) * max_boxes + slot] = c;
-    }
+    int slot = carry + (wid ? warp_sums[wid - 1] : 0) + v - cnt;
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (keepmask & (1 << e)) {
+        if (slot < max_boxes) {
+          const int q = q0 + e;
+          Component c;
+          c.root = q;
+          c.x = st.minx[base + q];
+          c.y = st.miny[base + q];
+          c.w = st.maxx[base + q] - c.x + 1;
+          c.h = st.maxy[base + q] - c.y + 1;
+          c.area = st.area[base + q];
+          comps[static_cast<size_t>(img) * max_boxes + slot] = c;
+        }
+        ++slot;
+      }
     __syncthreads();
     if (threadIdx.x == 0) carry += warp_sums[31];
     __syncthreads();

@@ -199,21 +199,23 @@ stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float*
     }
   __half* o = out + static_cast<size_t>(pix) * out_ld;
 #pragma unroll 1
-  for (int cb = 0; cb < 64; cb += 8) {
-    float acc[8];
+  for (int cb = 0; cb < 64; cb += 16) {                    // 16 channels = one 32-byte sector per 256-bit store
+    float acc[16];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = sb[cb + j];
+    for (int j = 0; j < 16; ++j) acc[j] = sb[cb + j];
 #pragma unroll
     for (int k = 0; k < 9; ++k)
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[j] = fmaf(v[k], sw[k * 64 + cb + j], acc[j]);
-    uint4 pk;
-    __half2 h;
-    h = __floats2half2_rn(fmaxf(acc[0], 0.f), fmaxf(acc[1], 0.f)); pk.x = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(fmaxf(acc[2], 0.f), fmaxf(acc[3], 0.f)); pk.y = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(fmaxf(acc[4], 0.f), fmaxf(acc[5], 0.f)); pk.z = *reinterpret_cast<uint32_t*>(&h);
-    h = __floats2half2_rn(fmaxf(acc[6], 0.f), fmaxf(acc[7], 0.f)); pk.w = *reinterpret_cast<uint32_t*>(&h);
-    *reinterpret_cast<uint4*>(o + cb) = pk;
+      for (int j = 0; j < 16; ++j) acc[j] = fmaf(v[k], sw[k * 64 + cb + j], acc[j]);
+    uint32_t pk[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __half2 h = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
+      pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+    }
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + cb), "r"(pk[0]), "r"(pk[1]),
+                 "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                 : "memory");
   }
 }
 

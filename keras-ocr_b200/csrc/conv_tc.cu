@@ -787,9 +787,14 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   memset(&p, 0, sizeof(p));
   p.N = in.n; p.H = in.h; p.W = in.w;
   p.cin = L.cin; p.cout = L.cout; p.ksize = L.ksize; p.dil = L.dil;
-  const double generic_cover = pick_box(in.n, in.h, in.w, &p.bw_log2, &p.bh_log2, &p.bn_log2);
-  // halo mode: 3x3, dilation 1, fixed 8 x 16 tile; skip it when that tile wastes >15 % more pixels
-  const double halo_cover = double((in.w + 7) / 8 * 8) * double((in.h + 15) / 16 * 16) * in.n;
+  pick_box(in.n, in.h, in.w, &p.bw_log2, &p.bh_log2, &p.bn_log2);
+  // halo mode: 3x3, dilation 1, fixed 8 x 16 tile; skip it when that tile wastes >15 % more pixels.  The two
+  // modes add the taps in different orders, so the choice must not depend on the batch size (a crop's result
+  // may not change with the batch it travels in): both covers are taken per image, as if N were unbounded.
+  int dw, dh, dn;
+  const double big_n = 1 << 20;
+  const double generic_cover = pick_box(1 << 20, in.h, in.w, &dw, &dh, &dn) / big_n;
+  const double halo_cover = double((in.w + 7) / 8 * 8) * double((in.h + 15) / 16 * 16);
   const bool want_pool = pool_out != nullptr;
   p.halo = (L.ksize == 3 && L.dil == 1 && ctx->conv_engine != B2O_CONV_TC_GENERIC &&
             (halo_cover <= 1.15 * generic_cover || want_pool)) ? 1 : 0;

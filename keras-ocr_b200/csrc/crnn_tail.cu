@@ -77,6 +77,53 @@ __global__ void stn_sample_kernel(const __half* __restrict__ feat, const float* 
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(pp) * C + cv * 8) = r;
 }
 
+// ---------------------------------------------------------------------------------------- STN conv_a tail
+// y: (B,50,7,512) fp16, column tap*16 + c = <x[pixel], W[tap][:, c]>; out[p][c] = relu(bias[c] + sum over the
+// 25 taps of y[p + offset(tap)][tap*16 + c]) with zero padding ("same", recognition.py:268-270).  One thread
+// per output pixel, taps added in (ky, kx) order in fp32.
+__global__ void stn_col2im_kernel(const __half* __restrict__ y, const float* __restrict__ bias, int B,
+                                  __half* __restrict__ out) {
+  constexpr int H = 50, W = 7;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= B * H * W) return;
+  const int w = p % W, h = (p / W) % H;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = bias[c];
+#pragma unroll
+  for (int ky = 0; ky < 5; ++ky) {
+    const int ih = h + ky - 2;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 5; ++kx) {
+      const int iw = w + kx - 2;
+      if (iw < 0 || iw >= W) continue;
+      const uint4* src = reinterpret_cast<const uint4*>(y + (static_cast<size_t>(p) + (ky - 2) * W + (kx - 2)) * 512 +
+                                                        (ky * 5 + kx) * 16);
+      const uint4 v0 = src[0], v1 = src[1];
+      const __half2* h0 = reinterpret_cast<const __half2*>(&v0);
+      const __half2* h1 = reinterpret_cast<const __half2*>(&v1);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 a = __half22float2(h0[e]), b = __half22float2(h1[e]);
+        acc[2 * e] += a.x; acc[2 * e + 1] += a.y;
+        acc[8 + 2 * e] += b.x; acc[8 + 2 * e + 1] += b.y;
+      }
+    }
+  }
+  uint4 o0, o1;
+  __half2* q0 = reinterpret_cast<__half2*>(&o0);
+  __half2* q1 = reinterpret_cast<__half2*>(&o1);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    q0[e] = __floats2half2_rn(fmaxf(acc[2 * e], 0.0f), fmaxf(acc[2 * e + 1], 0.0f));
+    q1[e] = __floats2half2_rn(fmaxf(acc[8 + 2 * e], 0.0f), fmaxf(acc[8 + 2 * e + 1], 0.0f));
+  }
+  uint4* dst = reinterpret_cast<uint4*>(out + static_cast<size_t>(p) * 16);
+  dst[0] = o0;
+  dst[1] = o1;
+}
+
 // ---------------------------------------------------------------------------------------- LSTM
 constexpr int kUnits = 128, kGates = 512, kSteps = 50;
 constexpr int kCropsPerCta = 8;
@@ -251,6 +298,13 @@ inline unsigned nb(long long total, int threads) { return static_cast<unsigned>(
 
 int stn_theta_run(b2o_ctx* ctx, const __half* d1, int B, float* theta, cudaStream_t st) {
   stn_theta_kernel<<<nb(B * 6, 128), 128, 0, st>>>(d1, B, ctx->stn_d2_w, ctx->stn_d2_b, theta);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+int stn_col2im_run(b2o_ctx* ctx, const __half* y, const float* bias, int B, __half* out, cudaStream_t st) {
+  const int total = B * 50 * 7;
+  stn_col2im_kernel<<<(total + 127) / 128, 128, 0, st>>>(y, bias, B, out);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

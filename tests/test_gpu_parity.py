@@ -433,6 +433,25 @@ def test_results_are_bit_reproducible(detector, recognizer):
         assert torch.equal(recognizer.tap("logits", (24, 48, 37), torch.float32), logits)
 
 
+def test_crop_result_does_not_depend_on_its_batch(recognizer):
+    """A crop's logits are bit-identical whatever batch it is recognised in (kernel configurations that change
+    the accumulation order are chosen from the per-image shape only)."""
+    rng = np.random.default_rng(3)
+    crops = torch.from_numpy(rng.integers(0, 256, (24, 31, 200), dtype=np.uint8)).to(recognizer.device)
+
+    def run(c):
+        n = c.shape[0]
+        x = torch.empty((n, 200, 31), dtype=torch.float16, device=recognizer.device)
+        recognizer.ctx.crops_to_input(c.contiguous().data_ptr(), n, x.data_ptr(), _stream())
+        labels = recognizer.predict_device(x).clone()
+        return labels, recognizer.tap("logits", (n, 48, 37), torch.float32).clone()
+
+    labels, logits = run(crops)
+    for lo, hi in ((0, 10), (10, 24), (3, 4), (5, 18)):
+        la, lg = run(crops[lo:hi])
+        assert torch.equal(lg, logits[lo:hi]) and torch.equal(la, labels[lo:hi])
+
+
 def test_pipelined_sub_batches_give_identical_results(cuda_device):
     """Pipeline(inflight=2) splits the batch into software-pipelined sub-batches; every (text, box) must equal
     the unsplit run exactly, for same-size arrays and for ragged lists (whole-batch padding is kept)."""
