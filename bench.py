@@ -184,6 +184,10 @@ def run_b200(args):
     pipe = Pipeline(detector=det, recognizer=rec, scale=SCALE, max_size=2048)
     pages = make_pages(rank)
     pages_dev = torch.from_numpy(pages).to(device)
+    # the e2e leg's inputs live in PINNED host memory (the contract's "from pinned host memory"); the numpy
+    # view below is what the user-facing call receives, and Pipeline uploads an already-pinned array as is
+    pages_pinned = torch.from_numpy(pages).pin_memory()
+    pages = pages_pinned.numpy()
     max_boxes = 128
     stats = {"words": 0}
 

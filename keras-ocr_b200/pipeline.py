@@ -50,7 +50,9 @@ class Pipeline:
         if self._h2d_stream is None:
             self._h2d_stream = torch.cuda.Stream(device=det.device)
         main = torch.cuda.current_stream(det.device)
-        pinned = torch.from_numpy(np.ascontiguousarray(array)).pin_memory()
+        pinned = torch.from_numpy(np.ascontiguousarray(array))
+        if not pinned.is_pinned():                       # callers that already hold pinned pages skip the staging copy
+            pinned = pinned.pin_memory()
         if self.inflight <= 1:                           # nothing queued to overlap with: plain stream-ordered copy
             return pinned.to(det.device, non_blocking=True)
         with torch.cuda.stream(self._h2d_stream):
