@@ -6,7 +6,8 @@
 One step = one ``recognize`` pass over a batch of 32 synthetic pages (768x768 RGB, 32 rendered
 words each, ``Pipeline(scale=2)`` -> 32x1536x1536 detector input, BASELINE.json configs[3]); with
 N GPUs every rank owns its own 32 pages (configs[4]: 256 pages over 8 GPUs, weak scaling) and the
-per-image (count, boxes, labels) records are gathered to rank 0 once per step.
+per-image (count, boxes, labels) records -- written on the device -- are gathered to rank 0 over NCCL
+once per step (``distributed.recognize_sharded``) and decoded there.
 
 Timed region: K steps bracketed by barrier + cuda synchronize, CUDA events, max over ranks.
 ``value``  : sources resident in HBM when the step starts (resize/pad ... CTC decode + result D2H).
@@ -191,23 +192,16 @@ def run_b200(args):
     max_boxes = 128
     stats = {"words": 0}
 
-    def gather(result):
-        if world == 1:
-            return
-        counts = [len(g) for g in result]
-        boxes = [np.array([b for _, b in g], dtype=np.float32).reshape(-1, 4, 2) for g in result]
-        labels = np.full((sum(counts), D.STEPS), -1, dtype=np.int8)
-        k = 0
-        for g in result:
-            for text, _ in g:
-                labels[k, :len(text)] = [rec.alphabet.index(ch) for ch in text]
-                k += 1
-        D.gather_records(D.pack_records(counts, boxes, labels, PAGES_PER_RANK, max_boxes), world, rank, device)
-
     def step(inputs):
-        result = pipe.recognize(inputs)
-        stats["words"] = sum(len(g) for g in result)
-        gather(result)
+        if world == 1:
+            result = pipe.recognize(inputs)
+        else:
+            # every rank runs its own 32 pages; the (count, boxes, labels) records are written on the device
+            # (b2o_pack_records), gathered to rank 0 in ONE NCCL gather and decoded there -- the other ranks
+            # never bring a result to the host
+            result = D.recognize_sharded(pipe, inputs, max_boxes=max_boxes, presharded=True)
+        if result is not None:
+            stats["words"] = sum(len(g) for g in result)
         return result
 
     def barrier():
@@ -241,6 +235,8 @@ def run_b200(args):
     ms_e2e = timed(pages, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     h2d, d2h = pipe.last_stats.get("h2d_bytes", 0), pipe.last_stats.get("d2h_bytes", 0)
+    if world > 1:                                        # rank 0 also reads the gathered record blocks
+        d2h += world * PAGES_PER_RANK * det.ctx.record_floats(max_boxes) * 4
 
     # roofline leg: one extra step with per-launch CUDA events around the tensor-core conv kernel
     det.ctx.profile_enable(1); rec.ctx.profile_enable(1)
@@ -282,7 +278,7 @@ def run_b200(args):
                      "flop_per_step": tc_flop, "kernel_ms_per_step": tc_ms,
                      "kernel_share_of_step": tc_ms / step_ms_plain if step_ms_plain > 0 else None,
                      "traffic": traffic},
-        "words_per_step_rank0": stats["words"],
+        "words_per_step": stats["words"],
     }
     if world == 1:
         v, desc, cores = cpu_sample(None, 1)

@@ -81,6 +81,12 @@ int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n);
 int b2o_resize_pad(b2o_ctx* ctx, const uint8_t* src_dev, int hs, int ws, int hr, int wr,
                    uint8_t* dst_dev, int index, int hp, int wp, void* stream);
 
+/* The same for a batch of n equally sized sources (n,hs,ws,3) in ONE launch (the 4-D ndarray input of
+ * pipeline.py:41-42).  gray, when not NULL, also receives cv2.cvtColor(RGB2GRAY) of the padded batch
+ * (n,hp,wp) -- recognition.py:510 -- so that the recognizer need not read the batch again.       */
+int b2o_resize_pad_batch(b2o_ctx* ctx, const uint8_t* src_dev, int n, int hs, int ws, int hr, int wr,
+                         uint8_t* dst_dev, int hp, int wp, uint8_t* gray_dev, void* stream);
+
 /* cv2.cvtColor(RGB2GRAY) (recognition.py:510) for a whole (n,h,w,3) batch -> (n,h,w).         */
 int b2o_rgb_to_gray(b2o_ctx* ctx, const uint8_t* img_dev, int n, int h, int w, uint8_t* gray_dev,
                     void* stream);
@@ -101,6 +107,14 @@ int b2o_get_boxes(b2o_ctx* ctx, const float* scores_dev, int n, int hs, int ws,
                   int size_threshold, float* boxes_dev, int32_t* counts_dev, int max_boxes,
                   void* ws_dev, size_t ws_bytes, void* stream);
 
+/* The box bookkeeping of recognize_from_boxes (recognition.py:511-521: crops are appended image after
+ * image, start_end = running offsets) on the device: the (n,max_boxes,4,2) table of b2o_get_boxes becomes
+ * the dense list flat (sum_i min(counts[i],max_boxes), 4, 2) with image_index[k] = image of box k, both
+ * sized for n*max_boxes entries by the caller.  Runs without the host knowing the counts, i.e. BEFORE
+ * the one synchronisation of the path.                                                          */
+int b2o_compact_boxes(b2o_ctx* ctx, const float* boxes_dev, const int32_t* counts_dev, int n, int max_boxes,
+                      float* flat_dev, int32_t* image_index_dev, void* stream);
+
 /* tools.warpBox over box groups (recognition.py:506-519; tools.py:61-117).  boxes: (n_boxes,4,2)
  * float32; image_index[k] selects the gray image of box k.  crops: (n_boxes,31,200) uint8
  * (exactly warpBox's output) and, when crnn_in != NULL, the CRNN input (n_boxes,200,31) fp16 =
@@ -116,6 +130,17 @@ size_t b2o_crnn_workspace_bytes(int b);
 int b2o_crops_to_input(b2o_ctx* ctx, const uint8_t* crops_dev, int b, void* crnn_in_dev, void* stream);
 int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in_dev, int b, int32_t* labels_dev,
                      void* ws_dev, size_t ws_bytes, void* stream);
+
+/* Result records of Pipeline.recognize for the multi-GPU gather (pipeline.py:66-75): one
+ * fixed-size float32 row per image = [count][rec_boxes x (4,2) boxes * inv_scale[i] (tools.adjust_boxes,
+ * tools.py:232-260)][rec_boxes x 48 labels as int8, -1 padded], b2o_record_floats(rec_boxes) floats long.
+ * boxes/counts as written by b2o_get_boxes, labels (sum counts, 48) int32 as written by b2o_crnn_forward
+ * (NULL when no image has a box).  Rows n..rows-1 (a short last shard) get count -1.  The class count
+ * must fit int8 (alphabets up to 126 characters).                                               */
+size_t b2o_record_floats(int rec_boxes);
+int b2o_pack_records(b2o_ctx* ctx, const float* boxes_dev, const int32_t* counts_dev, const int32_t* labels_dev,
+                     const float* inv_scale_dev, int n, int max_boxes, int rows, int rec_boxes,
+                     float* records_dev, void* stream);
 
 /* Debug / test taps (not on the product path): copy an intermediate of the last forward pass.
  * b2o_crnn_tap names: "features" (b,50,7,512 f16), "theta" (b,6 f32), "warped" (b,50,7,512 f16),

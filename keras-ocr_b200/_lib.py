@@ -41,11 +41,15 @@ SIGNATURES = {
     "b2o_load_craft": (_i, [_vp, _c.POINTER(_Tensor), _i]),
     "b2o_load_crnn": (_i, [_vp, _c.POINTER(_Tensor), _i]),
     "b2o_resize_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
+    "b2o_resize_pad_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
     "b2o_rgb_to_gray": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "b2o_craft_workspace_bytes": (_sz, [_i, _i, _i]),
     "b2o_craft_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
     "b2o_boxes_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "b2o_get_boxes": (_i, [_vp, _vp, _i, _i, _i, _f, _f, _f, _i, _vp, _vp, _i, _vp, _sz, _vp]),
+    "b2o_compact_boxes": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "b2o_record_floats": (_sz, [_i]),
+    "b2o_pack_records": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "b2o_warp_boxes": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
     "b2o_crnn_workspace_bytes": (_sz, [_i]),
     "b2o_crops_to_input": (_i, [_vp, _vp, _i, _vp, _vp]),
@@ -149,6 +153,10 @@ class Context:
     def resize_pad(self, src, hs, ws, hr, wr, dst, index, hp, wp, stream):
         self._check(self.lib.b2o_resize_pad(self.handle, src, hs, ws, hr, wr, dst, index, hp, wp, stream), "b2o_resize_pad")
 
+    def resize_pad_batch(self, src, n, hs, ws, hr, wr, dst, hp, wp, gray, stream):
+        self._check(self.lib.b2o_resize_pad_batch(self.handle, src, n, hs, ws, hr, wr, dst, hp, wp, gray, stream),
+                    "b2o_resize_pad_batch")
+
     def rgb_to_gray(self, img, n, h, w, gray, stream):
         self._check(self.lib.b2o_rgb_to_gray(self.handle, img, n, h, w, gray, stream), "b2o_rgb_to_gray")
 
@@ -164,6 +172,17 @@ class Context:
     def get_boxes(self, scores, n, hs, ws, det, text, link, size, boxes, counts, max_boxes, wsp, ws_bytes, stream):
         self._check(self.lib.b2o_get_boxes(self.handle, scores, n, hs, ws, det, text, link, size, boxes, counts,
                                            max_boxes, wsp, ws_bytes, stream), "b2o_get_boxes")
+
+    def compact_boxes(self, boxes, counts, n, max_boxes, flat, image_index, stream):
+        self._check(self.lib.b2o_compact_boxes(self.handle, boxes, counts, n, max_boxes, flat, image_index, stream),
+                    "b2o_compact_boxes")
+
+    def record_floats(self, rec_boxes):
+        return int(self.lib.b2o_record_floats(rec_boxes))
+
+    def pack_records(self, boxes, counts, labels, inv_scale, n, max_boxes, rows, rec_boxes, records, stream):
+        self._check(self.lib.b2o_pack_records(self.handle, boxes, counts, labels, inv_scale, n, max_boxes, rows,
+                                              rec_boxes, records, stream), "b2o_pack_records")
 
     def warp_boxes(self, gray, n, h, w, boxes, image_index, n_boxes, crops, crnn_in, stream):
         self._check(self.lib.b2o_warp_boxes(self.handle, gray, n, h, w, boxes, image_index, n_boxes, crops, crnn_in,

@@ -668,14 +668,110 @@ extern "C" int b2o_get_boxes(b2o_ctx* ctx, const float* scores, int n, int hs, i
   select_kernel<<<n, 1024, 0, st>>>(w.label, hs * ws, w.st, size_threshold, detection_threshold, w.comps, max_boxes,
                                     counts);
   B2O_LAUNCH_CHECK(ctx);
-  static bool configured = false;
   const int dyn = 2 * kQuadSmemPlaneWords * 4;
-  if (!configured) {
+  if (!ctx->quads_configured) {        // a per-device attribute, hence per context (one context per device)
     B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(quads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
-    configured = true;
+    ctx->quads_configured = true;
   }
   quads_kernel<<<dim3(max_boxes, n), 256, dyn, st>>>(w.mask, w.label, hs, ws, w.comps, counts, max_boxes, boxes,
                                                      w.big_planes, w.big_locks, kQuadSmemPlaneWords);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Box bookkeeping of recognize_from_boxes (recognition.py:511-521: crops appended image after image,
+// `start_end` = running offsets) and the result records of Pipeline.recognize (pipeline.py:66-75), done on
+// the device so that the host needs nothing but the per-image counts it already reads.
+namespace {
+
+// sum over images j < i of min(max(counts[j], 0), cap); every thread of the block gets the result
+__device__ int boxes_before(const int32_t* __restrict__ counts, int i, int cap) {
+  __shared__ int warp_sums[32];
+  __shared__ int total;
+  int s = 0;
+  for (int j = threadIdx.x; j < i; j += blockDim.x) s += min(max(counts[j], 0), cap);
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if ((threadIdx.x & 31) == 0) warp_sums[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    int v = threadIdx.x < (blockDim.x + 31) / 32 ? warp_sums[threadIdx.x] : 0;
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if (threadIdx.x == 0) total = v;
+  }
+  __syncthreads();
+  return total;
+}
+
+__global__ void __launch_bounds__(128)
+compact_boxes_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ counts, int max_boxes,
+                     float* __restrict__ flat, int32_t* __restrict__ image_index) {
+  const int i = blockIdx.x;
+  const int off = boxes_before(counts, i, max_boxes);
+  const int c = min(max(counts[i], 0), max_boxes);
+  const float4* src = reinterpret_cast<const float4*>(boxes + static_cast<size_t>(i) * max_boxes * 8);
+  float4* dst = reinterpret_cast<float4*>(flat + static_cast<size_t>(off) * 8);
+  for (int t = threadIdx.x; t < 2 * c; t += blockDim.x) dst[t] = src[t];
+  for (int t = threadIdx.x; t < c; t += blockDim.x) image_index[off + t] = i;
+}
+
+constexpr int kSteps = 48;                         // label steps per word (recognition.py:20: 50 - 2 discarded)
+
+__global__ void __launch_bounds__(128)
+pack_records_kernel(const float* __restrict__ boxes, const int32_t* __restrict__ counts,
+                    const int32_t* __restrict__ labels, const float* __restrict__ inv_scale, int n, int max_boxes,
+                    int rec_boxes, float* __restrict__ rec) {
+  const int row = blockIdx.x;
+  const int rec_len = 1 + rec_boxes * 8 + rec_boxes * (kSteps / 4);
+  float* r = rec + static_cast<size_t>(row) * rec_len;
+  int8_t* lab = reinterpret_cast<int8_t*>(r + 1 + rec_boxes * 8);
+  int c = 0, off = 0;
+  float inv = 1.f;
+  if (row < n) {                                   // uniform per block
+    off = boxes_before(counts, row, max_boxes);
+    c = min(min(max(counts[row], 0), max_boxes), rec_boxes);
+    inv = inv_scale[row];
+  }
+  if (threadIdx.x == 0) r[0] = row < n ? static_cast<float>(c) : -1.f;    // -1: padding row of a short shard
+  const float* src = boxes + static_cast<size_t>(min(row, n - 1)) * max_boxes * 8;
+  for (int t = threadIdx.x; t < rec_boxes * 8; t += blockDim.x)
+    r[1 + t] = t < c * 8 ? __fmul_rn(src[t], inv) : 0.f;                  // tools.adjust_boxes (tools.py:232-260)
+  for (int t = threadIdx.x; t < rec_boxes * kSteps; t += blockDim.x) {
+    const int k = t / kSteps;
+    lab[t] = (k < c && labels) ? static_cast<int8_t>(labels[static_cast<size_t>(off + k) * kSteps + (t - k * kSteps)])
+                   : static_cast<int8_t>(-1);
+  }
+}
+
+}  // namespace
+
+extern "C" int b2o_compact_boxes(b2o_ctx* ctx, const float* boxes, const int32_t* counts, int n, int max_boxes,
+                                 float* flat, int32_t* image_index, void* stream) {
+  if (!ctx) return B2O_ERR_ARG;
+  if (!boxes || !counts || !flat || !image_index || n <= 0 || max_boxes <= 0) {
+    ctx->set_error("b2o_compact_boxes: bad argument");
+    return B2O_ERR_ARG;
+  }
+  compact_boxes_kernel<<<n, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(boxes, counts, max_boxes, flat,
+                                                                            image_index);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+extern "C" size_t b2o_record_floats(int rec_boxes) {
+  return rec_boxes > 0 ? 1 + static_cast<size_t>(rec_boxes) * 8 + static_cast<size_t>(rec_boxes) * (kSteps / 4) : 0;
+}
+
+extern "C" int b2o_pack_records(b2o_ctx* ctx, const float* boxes, const int32_t* counts, const int32_t* labels,
+                                const float* inv_scale, int n, int max_boxes, int rows, int rec_boxes, float* records,
+                                void* stream) {
+  if (!ctx) return B2O_ERR_ARG;
+  if (!boxes || !counts || !inv_scale || !records || n <= 0 || rows < n || max_boxes <= 0 || rec_boxes <= 0) {
+    ctx->set_error("b2o_pack_records: bad argument");      // labels may be NULL when no image has a box
+    return B2O_ERR_ARG;
+  }
+  pack_records_kernel<<<rows, 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(boxes, counts, labels, inv_scale, n,
+                                                                              max_boxes, rec_boxes, records);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

@@ -70,6 +70,7 @@ struct b2o_ctx {
   std::string error;
   std::map<std::string, ConvLayer> craft, crnn;
   bool craft_loaded = false, crnn_loaded = false;
+  bool quads_configured = false;   // quads_kernel's dynamic shared-memory opt-in done on this device
   // CRNN tail parameters (device)
   float *stn_d2_w = nullptr, *stn_d2_b = nullptr;              // dense 64 -> 6, fp32
   __half* lstm_u[4] = {nullptr, nullptr, nullptr, nullptr};    // recurrent kernels [128][512] fp16

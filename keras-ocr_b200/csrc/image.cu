@@ -13,13 +13,26 @@
 namespace {
 
 // ------------------------------------------------------------------------------------ resize + pad
+// blockIdx.z = image of a batch of equally sized sources (strides 0 for the one-image entry point); `gray`,
+// when given, also receives cv2.cvtColor(RGB2GRAY) of the padded result (recognition.py:510), which saves the
+// recognizer a second pass over the batch.
+__device__ __forceinline__ uint8_t gray_of(int r, int g, int b) {
+  return static_cast<uint8_t>((9798 * r + 19235 * g + 3735 * b + 16384) >> 15);
+}
+
 __global__ void resize_pad_kernel(const uint8_t* __restrict__ src, int hs, int ws, int hr, int wr,
-                                  uint8_t* __restrict__ dst, int hp, int wp) {
+                                  uint8_t* __restrict__ dst, int hp, int wp, uint8_t* __restrict__ gray) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= wp) return;
-  uint8_t* o = dst + (static_cast<size_t>(y) * wp + x) * 3;
-  if (x >= wr || y >= hr) { o[0] = 255; o[1] = 255; o[2] = 255; return; }
+  src += static_cast<size_t>(blockIdx.z) * hs * ws * 3;
+  const size_t opix = (static_cast<size_t>(blockIdx.z) * hp + y) * wp + x;
+  uint8_t* o = dst + opix * 3;
+  if (x >= wr || y >= hr) {
+    o[0] = 255; o[1] = 255; o[2] = 255;
+    if (gray) gray[opix] = gray_of(255, 255, 255);
+    return;
+  }
   // OpenCV: scale = 1 / (dsize / ssize), source coordinate at pixel centres, float fractions,
   // 11-bit coefficients (INTER_RESIZE_COEF_BITS), horizontal pass first.
   const double scale_x = 1.0 / (static_cast<double>(wr) / ws);
@@ -38,13 +51,16 @@ __global__ void resize_pad_kernel(const uint8_t* __restrict__ src, int hs, int w
   const int y0 = min(max(sy, 0), hs - 1), y1 = min(max(sy + 1, 0), hs - 1);
   const uint8_t* r0 = src + static_cast<size_t>(y0) * ws * 3;
   const uint8_t* r1 = src + static_cast<size_t>(y1) * ws * 3;
+  int rgb[3];
 #pragma unroll
   for (int c = 0; c < 3; ++c) {
     const int s0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
     const int s1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
     const int v = (((b0 * (s0 >> 4)) >> 16) + ((b1 * (s1 >> 4)) >> 16) + 2) >> 2;
-    o[c] = static_cast<uint8_t>(min(max(v, 0), 255));
+    rgb[c] = min(max(v, 0), 255);
+    o[c] = static_cast<uint8_t>(rgb[c]);
   }
+  if (gray) gray[opix] = gray_of(rgb[0], rgb[1], rgb[2]);
 }
 
 // ------------------------------------------------------------------------------------ RGB -> gray
@@ -52,7 +68,7 @@ __global__ void gray_kernel(const uint8_t* __restrict__ img, long long total, ui
   const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= total) return;
   const uint8_t* q = img + p * 3;
-  gray[p] = static_cast<uint8_t>((9798 * q[0] + 19235 * q[1] + 3735 * q[2] + 16384) >> 15);
+  gray[p] = gray_of(q[0], q[1], q[2]);
 }
 
 // ------------------------------------------------------------------------------------ warpBox
@@ -234,7 +250,21 @@ extern "C" int b2o_resize_pad(b2o_ctx* ctx, const uint8_t* src, int hs, int ws, 
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   resize_pad_kernel<<<dim3((wp + 127) / 128, hp), 128, 0, st>>>(src, hs, ws, hr, wr,
-                                                                dst + static_cast<size_t>(index) * hp * wp * 3, hp, wp);
+                                                                dst + static_cast<size_t>(index) * hp * wp * 3, hp, wp,
+                                                                nullptr);
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+extern "C" int b2o_resize_pad_batch(b2o_ctx* ctx, const uint8_t* src, int n, int hs, int ws, int hr, int wr,
+                                    uint8_t* dst, int hp, int wp, uint8_t* gray, void* stream) {
+  if (!ctx) return B2O_ERR_ARG;
+  if (!src || !dst || n <= 0 || n > 65535 || hs <= 0 || ws <= 0 || hr <= 0 || wr <= 0 || hr > hp || wr > wp || hp > 65535) {
+    ctx->set_error("b2o_resize_pad_batch: bad argument (resized image must fit the padded size)");
+    return B2O_ERR_ARG;
+  }
+  resize_pad_kernel<<<dim3((wp + 127) / 128, hp, n), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, hs, ws, hr, wr, dst, hp, wp, gray);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

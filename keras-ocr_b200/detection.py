@@ -107,21 +107,28 @@ class Detector:
         counts_pin.copy_(counts, non_blocking=True)
         event = torch.cuda.Event()
         event.record(stream)
-        return {"scores": scores, "boxes": boxes, "counts_pin": counts_pin, "event": event, "m": m, "thr": thr}
+        # recognize_from_boxes' bookkeeping (dense box list + image index, recognition.py:511-521) is queued
+        # behind the counts copy: it needs no host knowledge, so it runs while the host still waits for the event
+        flat = torch.empty((n * m, 4, 2), dtype=torch.float32, device=self.device)
+        image_index = torch.empty((n * m,), dtype=torch.int32, device=self.device)
+        self.ctx.compact_boxes(boxes.data_ptr(), counts.data_ptr(), n, m, flat.data_ptr(), image_index.data_ptr(),
+                               stream.cuda_stream)
+        return {"scores": scores, "boxes": boxes, "counts": counts, "counts_pin": counts_pin, "event": event, "m": m,
+                "thr": thr, "flat": flat, "image_index": image_index}
 
     def boxes_finish(self, state):
         """Wait for ``boxes_enqueue``.  Returns (boxes (N,M,4,2) float32 CUDA, counts ndarray (N,)); re-runs
         getBoxes with a larger box table in the (rare) case an image had more boxes than the table holds."""
         state["event"].synchronize()                     # the one synchronisation of the detector half
         counts_host = state["counts_pin"].numpy().copy()
-        boxes = state["boxes"]
-        while counts_host.size and int(counts_host.max()) > boxes.shape[1]:
+        while counts_host.size and int(counts_host.max()) > state["boxes"].shape[1]:
             self.max_boxes = int(2 ** np.ceil(np.log2(int(counts_host.max()))))
             d, t, l, s = state["thr"]
             again = self.boxes_enqueue(state["scores"], d, t, l, s)
             again["event"].synchronize()
-            counts_host, boxes = again["counts_pin"].numpy().copy(), again["boxes"]
-        return boxes, counts_host
+            state.update(again)
+            counts_host = state["counts_pin"].numpy().copy()
+        return state["boxes"], counts_host
 
     def boxes_device(self, scores, detection_threshold=0.7, text_threshold=0.4, link_threshold=0.4,
                      size_threshold=10):

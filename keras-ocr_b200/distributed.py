@@ -44,16 +44,21 @@ def pack_records(counts, boxes, labels, per_rank, max_boxes):
 
 def unpack_records(rec, max_boxes):
     """Inverse of pack_records for one rank's block -> list of (count, boxes (c,4,2), labels (c,48))."""
-    rec = rec.cpu().numpy()
-    out = []
-    for row in rec:
-        c = int(row[0])
-        if c < 0:
-            continue
-        boxes = row[1:1 + c * 8].reshape(c, 4, 2).copy()
-        lab = np.ascontiguousarray(row[1 + max_boxes * 8:]).view(np.int8).reshape(max_boxes, STEPS)[:c].astype(np.int32)
-        out.append((c, boxes, lab))
-    return out
+    counts, boxes, labels = unpack_blocks([rec], max_boxes)
+    ends = np.cumsum(counts)
+    return [(int(c), boxes[e - c:e], labels[e - c:e].astype(np.int32)) for c, e in zip(counts, ends)]
+
+
+def unpack_blocks(blocks, max_boxes):
+    """All gathered blocks at once (rank order = global image order), vectorised: returns (counts (n_images,),
+    boxes (total,4,2) float32, labels (total,48) int8) with the words of image i at [sum(counts[:i]), +counts[i])."""
+    rec = np.concatenate([np.asarray(b.cpu() if isinstance(b, torch.Tensor) else b) for b in blocks], axis=0)
+    rec = rec[rec[:, 0] >= 0]                          # drop the padding rows of short shards
+    counts = rec[:, 0].astype(np.int64)
+    used = np.arange(max_boxes)[None, :] < counts[:, None]
+    boxes = rec[:, 1:1 + max_boxes * 8].reshape(-1, max_boxes, 4, 2)[used]
+    labels = np.ascontiguousarray(rec[:, 1 + max_boxes * 8:]).view(np.int8).reshape(-1, max_boxes, STEPS)[used]
+    return counts, boxes, labels
 
 
 def gather_records(local, world_size, rank, device=None):
@@ -67,19 +72,9 @@ def gather_records(local, world_size, rank, device=None):
     return blocks
 
 
-def recognize_sharded(pipeline, images, max_boxes=128):
-    """Run ``pipeline.recognize`` on this rank's shard of ``images`` and gather to rank 0.
-
-    Returns, on rank 0, the same list-of-lists as ``Pipeline.recognize`` for ALL images (global
-    order); ``None`` on the other ranks.  Boxes are in source-image pixels.
-    """
-    from . import recognition
-
-    world = dist.get_world_size() if dist.is_initialized() else 1
-    rank = dist.get_rank() if dist.is_initialized() else 0
-    lo, hi = shard_bounds(len(images), world, rank)
-    per_rank = shard_bounds(len(images), world, 0)[1]
-    local = pipeline.recognize(images[lo:hi]) if hi > lo else []
+def _host_records(pipeline, images, per_rank, max_boxes):
+    """Record block of a duck-typed pipeline: run its ``recognize`` and pack the (word, box) lists on the host."""
+    local = pipeline.recognize(images) if len(images) else []
     alphabet = pipeline.recognizer.alphabet
     counts = [len(g) for g in local]
     boxes = [np.array([b for _, b in g], dtype=np.float32).reshape(-1, 4, 2) for g in local]
@@ -89,13 +84,45 @@ def recognize_sharded(pipeline, images, max_boxes=128):
         for text, _ in g:
             labels[k, :len(text)] = [alphabet.index(ch) for ch in text]
             k += 1
-    device = pipeline.detector.device if dist.is_initialized() and dist.get_backend() == "nccl" else None
-    blocks = gather_records(pack_records(counts, boxes, labels, per_rank, max_boxes), world, rank, device)
+    return pack_records(counts, boxes, labels, per_rank, max_boxes)
+
+
+def recognize_sharded(pipeline, images, max_boxes=128, presharded=False):
+    """Run ``pipeline.recognize`` on this rank's shard of ``images`` and gather to rank 0.
+
+    ``images`` is the global batch (every rank passes the same list and takes its contiguous slice) or, with
+    ``presharded=True``, this rank's own slice (equal length on every rank).  A pipeline that offers
+    ``recognize_records`` (this package's ``Pipeline`` with its own Detector / Recognizer) never brings its
+    results to the host: the record block is written by ``b2o_pack_records`` on the device, gathered over
+    NCCL/NVLink, and copied to the host once, on rank 0.  Any other pipeline goes through ``recognize`` and
+    ``pack_records``.
+
+    Returns, on rank 0, the same list-of-lists as ``Pipeline.recognize`` for ALL images (global
+    order); ``None`` on the other ranks.  Boxes are in source-image pixels.
+    """
+    from . import recognition
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    if presharded:
+        mine, per_rank = images, len(images)
+    else:
+        lo, hi = shard_bounds(len(images), world, rank)
+        mine, per_rank = images[lo:hi], shard_bounds(len(images), world, 0)[1]
+    alphabet = pipeline.recognizer.alphabet
+    assert len(alphabet) + 1 <= 127, "record labels travel as int8: alphabets up to 126 characters"
+    if per_rank == 0:
+        return [] if rank == 0 else None
+    if getattr(pipeline, "recognize_records", None) is not None and getattr(pipeline, "_native", lambda: True)():
+        local = pipeline.recognize_records(mine, rows=per_rank, rec_boxes=max_boxes)
+        device = None                                   # already where the backend wants it
+    else:
+        local = _host_records(pipeline, mine, per_rank, max_boxes)
+        device = pipeline.detector.device if dist.is_initialized() and dist.get_backend() == "nccl" else None
+    blocks = gather_records(local, world, rank, device)
     if rank != 0:
         return None
-    out = []
-    for block in blocks:
-        for c, bx, lab in unpack_records(block, max_boxes):
-            texts = recognition.labels_to_text(lab, alphabet)
-            out.append(list(zip(texts, bx)))
-    return out
+    counts, boxes, labels = unpack_blocks(blocks, max_boxes)
+    texts = recognition.labels_to_text(labels, alphabet)
+    ends = np.cumsum(counts)
+    return [list(zip(texts[e - c:e], boxes[e - c:e])) for c, e in zip(counts, ends)]

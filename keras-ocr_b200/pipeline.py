@@ -63,47 +63,62 @@ class Pipeline:
         main.wait_event(done)
         return t
 
-    def prepare_device(self, images, pad_to=None):
-        """resize_image + pad (pipeline.py:44-57) on the GPU.  Returns ((N,H,W,3) u8 CUDA tensor, scales).
+    def _plans(self, images):
+        """(scale, height, width) after tools.resize_image for every image (one rule for a 4-D batch)."""
+        if isinstance(images, (np.ndarray, torch.Tensor)) and images.ndim == 4:
+            return [tools.resize_plan(tuple(images.shape[1:]), self.scale, self.max_size)] * len(images)
+        return [tools.resize_plan(tuple(image.shape), self.scale, self.max_size) for image in images]
+
+    def prepare_device(self, images, pad_to=None, want_gray=False):
+        """resize_image + pad (pipeline.py:44-57) on the GPU.  Returns ((N,H,W,3) u8 CUDA tensor, scales), plus
+        the gray batch (N,H,W) u8 (recognition.py:510) or None when ``want_gray``: equally sized sources (a 4-D
+        array / tensor) are resized in ONE launch that also writes the gray image the recognizer needs.
         ``pad_to``: (height, width) of the padded batch when ``images`` is part of a larger batch."""
         det = self.detector
-        plans = [tools.resize_plan(image.shape, self.scale, self.max_size) for image in images]
+        plans = self._plans(images)
         scales = [p[0] for p in plans]
         hp, wp = pad_to if pad_to is not None else (max(p[1] for p in plans), max(p[2] for p in plans))
         n = len(images)
         stream = torch.cuda.current_stream(det.device).cuda_stream
         batch = torch.empty((n, hp, wp, 3), dtype=torch.uint8, device=det.device)
         same = isinstance(images, np.ndarray) and images.ndim == 4
-        h2d = 0
+        h2d, gray = 0, None
         if isinstance(images, torch.Tensor):
             # sources already resident in HBM (bench.py's device-resident leg): no copy
             assert images.is_cuda and images.dtype == torch.uint8 and images.dim() == 4
             src_all, same = images.contiguous(), True
         elif same:
+            assert images.shape[3] == 3 and images.dtype == np.uint8, "images must be HxWx3 uint8"
             src_all = self._upload(images)
             h2d = src_all.numel()
-        for i, image in enumerate(images):
-            if same:
-                src = src_all[i]
-            else:
+        if same:
+            _, hr, wr = plans[0]
+            gray = torch.empty((n, hp, wp), dtype=torch.uint8, device=det.device)
+            det.ctx.resize_pad_batch(src_all.data_ptr(), n, src_all.shape[1], src_all.shape[2], hr, wr, batch.data_ptr(),
+                                     hp, wp, gray.data_ptr(), stream)
+        else:
+            for i, image in enumerate(images):
                 assert image.ndim == 3 and image.shape[2] == 3 and image.dtype == np.uint8, "images must be HxWx3 uint8"
                 src = self._upload(image)
                 h2d += src.numel()
-            _, hr, wr = plans[i]
-            det.ctx.resize_pad(src.data_ptr(), image.shape[0], image.shape[1], hr, wr, batch.data_ptr(), i, hp, wp, stream)
+                _, hr, wr = plans[i]
+                det.ctx.resize_pad(src.data_ptr(), image.shape[0], image.shape[1], hr, wr, batch.data_ptr(), i, hp, wp, stream)
         self.last_stats["h2d_bytes"] = self.last_stats.get("h2d_bytes", 0) + int(h2d)
-        return batch, scales
+        return (batch, scales, gray) if want_gray else (batch, scales)
 
     # ---------------------------------------------------------------- the three stages of one sub-batch
     def _stage_detect(self, images, pad_to, thresholds):
-        batch, scales = self.prepare_device(images, pad_to)
+        batch, scales, gray = self.prepare_device(images, pad_to, want_gray=True)
         scores = self.detector.predict_device(batch)
-        return {"batch": batch, "scales": scales, "boxes_state": self.detector.boxes_enqueue(scores, **thresholds)}
+        return {"batch": batch, "scales": scales, "gray": gray,
+                "boxes_state": self.detector.boxes_enqueue(scores, **thresholds)}
 
     def _stage_recognize(self, st):
         det, rec = self.detector, self.recognizer
-        boxes, counts = det.boxes_finish(st.pop("boxes_state"))
-        labels = rec.recognize_from_boxes_device(st["batch"], boxes, counts)
+        bst = st.pop("boxes_state")
+        boxes, counts = det.boxes_finish(bst)
+        labels = rec.recognize_from_boxes_device(st["batch"], boxes, counts, gray=st["gray"], flat=bst["flat"],
+                                                 image_index=bst["image_index"])
         st["counts"] = counts
         st["boxes_host"] = torch.empty(boxes.shape, dtype=boxes.dtype, pin_memory=True)
         st["boxes_host"].copy_(boxes, non_blocking=True)
@@ -155,7 +170,7 @@ class Pipeline:
         self.last_stats = {"h2d_bytes": 0, "d2h_bytes": 0}
         if n == 0:
             return []
-        plans = [tools.resize_plan(image.shape, self.scale, self.max_size) for image in images]
+        plans = self._plans(images)
         pad_to = (max(p[1] for p in plans), max(p[2] for p in plans))      # of the WHOLE batch (pipeline.py:48-57)
         k = max(1, min(int(self.inflight), n // self.min_chunk))
         bounds = [n * i // k for i in range(k + 1)]
@@ -169,6 +184,40 @@ class Pipeline:
                 out.extend(self._stage_finish(states[step - 2]))
                 states[step - 2] = None
         return out
+
+    def recognize_records(self, images, rows=None, rec_boxes=128, detection_kwargs=None):
+        """``recognize`` without the trip to the host: returns the results as a CUDA float32 tensor of fixed-size
+        per-image records, ``(rows, b2o_record_floats(rec_boxes))`` = [count | rec_boxes x (4,2) boxes in source
+        pixels | rec_boxes x 48 int8 labels] (``distributed.unpack_blocks`` decodes it; rows beyond ``len(images)``
+        carry count -1).  This is the payload of the multi-GPU gather: only the per-image box
+        counts ever reach the host on this rank."""
+        assert self._native(), "recognize_records needs this package's Detector and Recognizer"
+        if not isinstance(images, (np.ndarray, torch.Tensor)):
+            images = [tools.read(image) for image in images]
+        det, rec = self.detector, self.recognizer
+        thresholds = {k: v for k, v in (detection_kwargs or {}).items()
+                      if k in ("detection_threshold", "text_threshold", "link_threshold", "size_threshold")}
+        n = len(images)
+        rows = n if rows is None else int(rows)
+        assert rows >= n and rows > 0
+        self.last_stats = {"h2d_bytes": 0, "d2h_bytes": 0}
+        records = torch.empty((rows, det.ctx.record_floats(rec_boxes)), dtype=torch.float32, device=det.device)
+        if n == 0:
+            records.zero_()
+            records[:, 0] = -1
+            return records
+        plans = self._plans(images)
+        st = self._stage_detect(images, (max(p[1] for p in plans), max(p[2] for p in plans)), thresholds)
+        bst = st.pop("boxes_state")
+        boxes, counts = det.boxes_finish(bst)
+        labels = rec.recognize_from_boxes_device(st["batch"], boxes, counts, gray=st["gray"], flat=bst["flat"],
+                                                 image_index=bst["image_index"])
+        inv = torch.tensor([1.0 / s for s in st["scales"]], dtype=torch.float32).to(det.device, non_blocking=True)
+        det.ctx.pack_records(boxes.data_ptr(), bst["counts"].data_ptr(), labels.data_ptr() if labels is not None else None,
+                             inv.data_ptr(), n, boxes.shape[1], rows, rec_boxes, records.data_ptr(),
+                             torch.cuda.current_stream(det.device).cuda_stream)
+        self.last_stats["d2h_bytes"] = int(counts.nbytes)
+        return records
 
     def _recognize_generic(self, images, detection_kwargs, recognition_kwargs):
         """Reference flow for injected (duck-typed) detectors / recognizers: host arrays between stages."""

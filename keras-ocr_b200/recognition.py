@@ -145,18 +145,27 @@ class Recognizer:
             image = cv2.cvtColor(image, code=cv2.COLOR_RGB2GRAY)
         return self.recognize_crops(np.ascontiguousarray(image.reshape(1, TARGET_HEIGHT, TARGET_WIDTH)))[0]
 
-    def recognize_from_boxes_device(self, images_t, boxes, counts):
-        """images_t (N,H,W,3) u8 CUDA; boxes (N,M,4,2) f32 CUDA; counts host ndarray -> labels (B,48) i32 CUDA."""
+    def recognize_from_boxes_device(self, images_t, boxes, counts, gray=None, flat=None, image_index=None):
+        """images_t (N,H,W,3) u8 CUDA; boxes (N,M,4,2) f32 CUDA; counts host ndarray -> labels (B,48) i32 CUDA.
+
+        Optional device-side by-products of the earlier stages, so that nothing but the kernel launches is
+        left to do once the host knows the counts: ``gray`` (N,H,W) u8 from ``b2o_resize_pad_batch``;
+        ``flat`` (>=B,4,2) / ``image_index`` (>=B,) from ``b2o_compact_boxes``."""
         counts = np.asarray(counts)
-        total = int(counts.sum())
+        m = boxes.shape[1]
+        total = int(np.minimum(counts, m).sum())
         if total == 0:
             return None
-        idx = np.repeat(np.arange(len(counts), dtype=np.int32), counts)
-        image_index = torch.from_numpy(idx).to(self.device, non_blocking=True)
-        m = boxes.shape[1]
-        slot = np.concatenate([np.arange(c, dtype=np.int64) for c in counts]) + idx.astype(np.int64) * m
-        flat = boxes.reshape(-1, 4, 2).index_select(0, torch.from_numpy(slot).to(self.device, non_blocking=True)).contiguous()
-        crnn_in, _ = self.warp_device(self.gray_device(images_t), flat, image_index)
+        if gray is None:
+            gray = self.gray_device(images_t)
+        if flat is None or image_index is None:
+            n = len(counts)
+            flat = torch.empty((n * m, 4, 2), dtype=torch.float32, device=self.device)
+            image_index = torch.empty((n * m,), dtype=torch.int32, device=self.device)
+            counts_dev = torch.from_numpy(counts.astype(np.int32)).to(self.device)
+            self.ctx.compact_boxes(boxes.data_ptr(), counts_dev.data_ptr(), n, m, flat.data_ptr(),
+                                   image_index.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        crnn_in, _ = self.warp_device(gray, flat[:total], image_index[:total])
         return self.predict_device(crnn_in)
 
     # ------------------------------------------------------------------ reference API

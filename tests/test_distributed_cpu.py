@@ -3,6 +3,7 @@ import os
 import socket
 
 import numpy as np
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -49,12 +50,26 @@ class _FakePipeline:
         return out
 
 
-def _worker(rank, world, port, images, ret):
+class _FakeRecordsPipeline(_FakePipeline):
+    """Also offers ``recognize_records`` (the device-record path of the real Pipeline), here built on the host."""
+    calls = 0
+
+    def recognize_records(self, images, rows=None, rec_boxes=128):
+        type(self).calls += 1
+        return D._host_records(_FakePipeline(), images, rows, rec_boxes)
+
+
+def _worker(rank, world, port, images, ret, kind="host", presharded=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        res = D.recognize_sharded(_FakePipeline(), images, max_boxes=8)
+        pipe = _FakeRecordsPipeline() if kind == "records" else _FakePipeline()
+        if presharded:                                  # every rank brings its own, equally long, slice
+            images = images[rank * 3:(rank + 1) * 3]
+        res = D.recognize_sharded(pipe, images, max_boxes=8, presharded=presharded)
+        if kind == "records":
+            assert _FakeRecordsPipeline.calls == 1
         if rank == 0:
             ret.put([[(t, b.tolist()) for t, b in g] for g in res])
         else:
@@ -63,18 +78,34 @@ def _worker(rank, world, port, images, ret):
         dist.destroy_process_group()
 
 
-def test_recognize_sharded_world2_gloo():
+@pytest.mark.parametrize("kind,presharded", [("host", False), ("records", False), ("records", True)])
+def test_recognize_sharded_world2_gloo(kind, presharded):
     images = np.zeros((7, 4, 4, 3), np.uint8)
     images[:, 0, 0, 0] = np.arange(7) + 1
     s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
     ctx = mp.get_context("spawn")
     ret = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, images, ret)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, images, ret, kind, presharded)) for r in range(2)]
     for p in procs:
         p.start()
     got = ret.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    expect = [[(t, b.tolist()) for t, b in g] for g in _FakePipeline().recognize(images)]
+    covered = images[:6] if presharded else images     # two ranks x three images when every rank brings its own
+    expect = [[(t, b.tolist()) for t, b in g] for g in _FakePipeline().recognize(covered)]
     assert got == expect                       # global order preserved, payload bit-exact
+
+
+def test_unpack_blocks_matches_per_block_unpack():
+    rng = np.random.default_rng(1)
+    blocks, expect = [], []
+    for per_rank, counts in ((3, [2, 0, 8]), (3, [1, 5])):       # second block is a short shard (one padding row)
+        boxes = [rng.uniform(0, 900, (c, 4, 2)).astype(np.float32) for c in counts]
+        labels = rng.integers(-1, 37, (sum(counts), 48)).astype(np.int8)
+        blocks.append(D.pack_records(counts, boxes, labels, per_rank, 8))
+        expect += D.unpack_records(blocks[-1], 8)
+    counts, boxes, labels = D.unpack_blocks(blocks, 8)
+    assert counts.tolist() == [2, 0, 8, 1, 5] == [e[0] for e in expect]
+    assert np.array_equal(boxes, np.concatenate([e[1] for e in expect]))
+    assert np.array_equal(labels.astype(np.int32), np.concatenate([e[2] for e in expect]))

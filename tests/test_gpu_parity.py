@@ -484,3 +484,135 @@ def test_recognizer_single_crop_api(recognizer):
     gray = cv2.cvtColor(fitted, cv2.COLOR_RGB2GRAY)
     assert text == recognizer.recognize_crops(gray[None])[0]
     assert isinstance(text, str)
+
+
+# ------------------------------------------------------------------------------- batch entry points / records
+def test_resize_pad_batch_and_fused_gray_bit_exact(ctx, cuda_device):
+    """b2o_resize_pad_batch (one launch for equally sized sources, gray fused) == per-image b2o_resize_pad
+    followed by b2o_rgb_to_gray, and the gray plane == cv2.cvtColor of the padded batch (oracle)."""
+    from oracle import imageops
+    rng = np.random.default_rng(5)
+    n, hs, ws, hr, wr, hp, wp = 3, 45, 67, 90, 134, 96, 141
+    src = torch.from_numpy(rng.integers(0, 256, (n, hs, ws, 3), dtype=np.uint8)).to(cuda_device)
+    one = torch.zeros((n, hp, wp, 3), dtype=torch.uint8, device=cuda_device)
+    for i in range(n):
+        ctx.resize_pad(src[i].data_ptr(), hs, ws, hr, wr, one.data_ptr(), i, hp, wp, _stream())
+    gray_one = torch.empty((n, hp, wp), dtype=torch.uint8, device=cuda_device)
+    ctx.rgb_to_gray(one.data_ptr(), n, hp, wp, gray_one.data_ptr(), _stream())
+    batch = torch.zeros_like(one)
+    gray = torch.zeros_like(gray_one)
+    ctx.resize_pad_batch(src.data_ptr(), n, hs, ws, hr, wr, batch.data_ptr(), hp, wp, gray.data_ptr(), _stream())
+    assert torch.equal(batch, one) and torch.equal(gray, gray_one)
+    assert np.array_equal(gray.cpu().numpy(), np.stack([imageops.rgb_to_gray(i) for i in one.cpu().numpy()]))
+    again = torch.zeros_like(one)                                   # gray is optional
+    ctx.resize_pad_batch(src.data_ptr(), n, hs, ws, hr, wr, again.data_ptr(), hp, wp, None, _stream())
+    assert torch.equal(again, one)
+    with pytest.raises(_lib.B2OError):
+        ctx.resize_pad_batch(src.data_ptr(), n, hs, ws, hr, wr, again.data_ptr(), hr - 1, wp, None, _stream())
+
+
+def test_compact_boxes_and_pack_records_match_host_bookkeeping(ctx, cuda_device):
+    """b2o_compact_boxes == the running-offset bookkeeping of recognize_from_boxes (recognition.py:511-521);
+    b2o_pack_records == distributed.pack_records (the host packer, itself round-trip tested on the CPU), bit for
+    bit, including clamped counts, empty images and the padding rows of a short shard."""
+    from keras_ocr_b200 import distributed as D
+    rng = np.random.default_rng(9)
+    n, m, rows, rec_boxes = 5, 8, 7, 6
+    counts = np.array([3, 0, 8, 11, 1], np.int32)                    # 11 > m: the table holds only 8
+    held = np.minimum(counts, m)
+    boxes = rng.uniform(0, 3000, (n, m, 4, 2)).astype(np.float32)
+    total = int(held.sum())
+    labels = rng.integers(-1, 37, (total, 48)).astype(np.int32)
+    inv = np.array([0.5, 1.0, 1 / 1.6, 0.5, 1 / 3], np.float32)
+    b_t, c_t = torch.from_numpy(boxes).to(cuda_device), torch.from_numpy(counts).to(cuda_device)
+    flat = torch.zeros((n * m, 4, 2), dtype=torch.float32, device=cuda_device)
+    index = torch.full((n * m,), -7, dtype=torch.int32, device=cuda_device)
+    ctx.compact_boxes(b_t.data_ptr(), c_t.data_ptr(), n, m, flat.data_ptr(), index.data_ptr(), _stream())
+    assert np.array_equal(flat.cpu().numpy()[:total], np.concatenate([boxes[i, :held[i]] for i in range(n)]))
+    assert np.array_equal(index.cpu().numpy()[:total], np.repeat(np.arange(n), held))
+    assert (index.cpu().numpy()[total:] == -7).all()                 # nothing written past the dense list
+
+    rec = torch.zeros((rows, ctx.record_floats(rec_boxes)), dtype=torch.float32, device=cuda_device)
+    ctx.pack_records(b_t.data_ptr(), c_t.data_ptr(), torch.from_numpy(labels).to(cuda_device).data_ptr(),
+                     torch.from_numpy(inv).to(cuda_device).data_ptr(), n, m, rows, rec_boxes, rec.data_ptr(), _stream())
+    scaled = [boxes[i, :held[i]] * inv[i] for i in range(n)]         # tools.adjust_boxes: float32 * float32
+    expect = D.pack_records(held, scaled, labels.astype(np.int8), rows, rec_boxes)
+    assert np.array_equal(rec.cpu().numpy().view(np.uint32), expect.numpy().view(np.uint32))
+    got_counts, got_boxes, got_labels = D.unpack_blocks([rec], rec_boxes)
+    assert got_counts.tolist() == np.minimum(held, rec_boxes).tolist()
+
+
+def test_recognize_records_equals_recognize(cuda_device):
+    """Pipeline.recognize_records (results stay on the device as records; the multi-GPU payload) decodes to exactly
+    what Pipeline.recognize returns: same words, boxes bit-identical, padding rows ignored."""
+    from keras_ocr_b200 import distributed as D, recognition
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import synth
+    pipe = Pipeline(detector=Detector(weights=W.synthetic_craft_weights(3, textlike=True)),
+                    recognizer=Recognizer(weights=W.synthetic_crnn_weights(2)), scale=2, max_size=600)
+    pages, _ = synth.text_images(seed=5, n=3, h=192, w=384, n_words=4)      # 384 * 2 > 600: scale 1.5625
+    pages = np.concatenate([pages, np.full((1, 192, 384, 3), 255, np.uint8)])      # plus a blank page
+    ref = pipe.recognize(pages)
+    assert sum(len(g) for g in ref) >= 6 and ref[3] == []
+    rec = pipe.recognize_records(pages, rows=6, rec_boxes=16)
+    assert rec.is_cuda and rec.shape == (6, pipe.detector.ctx.record_floats(16))
+    counts, boxes, labels = D.unpack_blocks([rec], 16)
+    assert counts.tolist() == [len(g) for g in ref]
+    texts = recognition.labels_to_text(labels, pipe.recognizer.alphabet)
+    assert texts == [t for g in ref for t, _ in g]
+    assert np.array_equal(boxes, np.concatenate([np.stack([b for _, b in g]) for g in ref if g]))
+    # the one-process form of the sharded call goes through the same records
+    assert [[t for t, _ in g] for g in D.recognize_sharded(pipe, pages, max_boxes=16)] == [[t for t, _ in g] for g in ref]
+
+
+# ------------------------------------------------------------------------------- BASELINE.json sizes: properties
+def test_full_size_page_results_do_not_depend_on_the_batch(cuda_device):
+    """configs[3] geometry (768x768 sources, scale 2 -> 1536x1536 detector input, 32 words per page) on a small
+    batch: every rendered word is found, and a page's (word, box) list is bit-identical whether the page is
+    recognised alone or inside a batch (images are independent, pipeline.py:28-75)."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import synth
+    pipe = Pipeline(detector=Detector(weights=W.synthetic_craft_weights(3, textlike=True)),
+                    recognizer=Recognizer(weights=W.synthetic_crnn_weights(2)), scale=2)
+    pages, _ = synth.text_images(seed=1000, n=3, h=768, w=768, n_words=32)
+    together = pipe.recognize(pages)
+    assert [len(g) for g in together] == [32, 32, 32] or min(len(g) for g in together) >= 30
+    for i in (0, 2):
+        alone = pipe.recognize(pages[i:i + 1])[0]
+        assert [t for t, _ in alone] == [t for t, _ in together[i]]
+        assert all(np.array_equal(a, b) for (_, a), (_, b) in zip(alone, together[i]))
+
+
+def test_craft_batch8_768_scores_do_not_depend_on_the_batch(detector):
+    """configs[1] (CRAFT only, batch 8 at 768x768): image i of the batch gives bit-identical score maps to image i
+    alone, and the maps are finite."""
+    rng = np.random.default_rng(4)
+    img = torch.from_numpy(rng.integers(0, 256, (8, 768, 768, 3), dtype=np.uint8)).to(detector.device)
+    scores = detector.predict_device(img).clone()
+    assert scores.shape == (8, 384, 384, 2) and bool(torch.isfinite(scores).all())
+    for i in (0, 5, 7):
+        assert torch.equal(detector.predict_device(img[i:i + 1].contiguous())[0], scores[i])
+
+
+def test_crnn_batch256_labels_do_not_depend_on_the_batch(recognizer):
+    """configs[2] (CRNN only, 256 crops 31x200 + greedy CTC): labels of a crop are the same in the batch of 256
+    and in a sub-batch; rows are -1 padded after the decoded prefix and never contain the blank."""
+    rng = np.random.default_rng(6)
+    crops = torch.from_numpy(rng.integers(0, 256, (256, 31, 200), dtype=np.uint8)).to(recognizer.device)
+
+    def run(c):
+        x = torch.empty((c.shape[0], 200, 31), dtype=torch.float16, device=recognizer.device)
+        recognizer.ctx.crops_to_input(c.contiguous().data_ptr(), c.shape[0], x.data_ptr(), _stream())
+        return recognizer.predict_device(x).clone()
+
+    labels = run(crops)
+    assert labels.shape == (256, 48)
+    assert torch.equal(run(crops[100:133]), labels[100:133])
+    lab = labels.cpu().numpy()
+    assert ((lab >= -1) & (lab < 36)).all()
+    pad = lab == -1
+    assert (pad[:, :-1] <= pad[:, 1:]).all()                        # once padding starts it continues
