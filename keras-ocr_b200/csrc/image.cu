@@ -20,8 +20,11 @@ __device__ __forceinline__ uint8_t gray_of(int r, int g, int b) {
   return static_cast<uint8_t>((9798 * r + 19235 * g + 3735 * b + 16384) >> 15);
 }
 
+// scale_x / scale_y = 1 / (dsize / ssize) in fp64, computed once on the host exactly as OpenCV does: two fp64
+// divisions per pixel cost more than everything else in this kernel.
 __global__ void resize_pad_kernel(const uint8_t* __restrict__ src, int hs, int ws, int hr, int wr,
-                                  uint8_t* __restrict__ dst, int hp, int wp, uint8_t* __restrict__ gray) {
+                                  uint8_t* __restrict__ dst, int hp, int wp, uint8_t* __restrict__ gray,
+                                  double scale_x, double scale_y) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int y = blockIdx.y;
   if (x >= wp) return;
@@ -35,8 +38,6 @@ __global__ void resize_pad_kernel(const uint8_t* __restrict__ src, int hs, int w
   }
   // OpenCV: scale = 1 / (dsize / ssize), source coordinate at pixel centres, float fractions,
   // 11-bit coefficients (INTER_RESIZE_COEF_BITS), horizontal pass first.
-  const double scale_x = 1.0 / (static_cast<double>(wr) / ws);
-  const double scale_y = 1.0 / (static_cast<double>(hr) / hs);
   float fx = static_cast<float>((x + 0.5) * scale_x - 0.5);
   int sx = static_cast<int>(floorf(fx));
   fx -= sx;
@@ -251,7 +252,8 @@ extern "C" int b2o_resize_pad(b2o_ctx* ctx, const uint8_t* src, int hs, int ws, 
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   resize_pad_kernel<<<dim3((wp + 127) / 128, hp), 128, 0, st>>>(src, hs, ws, hr, wr,
                                                                 dst + static_cast<size_t>(index) * hp * wp * 3, hp, wp,
-                                                                nullptr);
+                                                                nullptr, 1.0 / (static_cast<double>(wr) / ws),
+                                                                1.0 / (static_cast<double>(hr) / hs));
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }
@@ -264,7 +266,7 @@ extern "C" int b2o_resize_pad_batch(b2o_ctx* ctx, const uint8_t* src, int n, int
     return B2O_ERR_ARG;
   }
   resize_pad_kernel<<<dim3((wp + 127) / 128, hp, n), 128, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      src, hs, ws, hr, wr, dst, hp, wp, gray);
+      src, hs, ws, hr, wr, dst, hp, wp, gray, 1.0 / (static_cast<double>(wr) / ws), 1.0 / (static_cast<double>(hr) / hs));
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

@@ -533,8 +533,9 @@ def test_compact_boxes_and_pack_records_match_host_bookkeeping(ctx, cuda_device)
     assert (index.cpu().numpy()[total:] == -7).all()                 # nothing written past the dense list
 
     rec = torch.zeros((rows, ctx.record_floats(rec_boxes)), dtype=torch.float32, device=cuda_device)
-    ctx.pack_records(b_t.data_ptr(), c_t.data_ptr(), torch.from_numpy(labels).to(cuda_device).data_ptr(),
-                     torch.from_numpy(inv).to(cuda_device).data_ptr(), n, m, rows, rec_boxes, rec.data_ptr(), _stream())
+    labels_t, inv_t = torch.from_numpy(labels).to(cuda_device), torch.from_numpy(inv).to(cuda_device)
+    ctx.pack_records(b_t.data_ptr(), c_t.data_ptr(), labels_t.data_ptr(), inv_t.data_ptr(), n, m, rows, rec_boxes,
+                     rec.data_ptr(), _stream())
     scaled = [boxes[i, :held[i]] * inv[i] for i in range(n)]         # tools.adjust_boxes: float32 * float32
     expect = D.pack_records(held, scaled, labels.astype(np.int8), rows, rec_boxes)
     assert np.array_equal(rec.cpu().numpy().view(np.uint32), expect.numpy().view(np.uint32))
