@@ -152,22 +152,18 @@ stem_rgb_kernel(const uint8_t* __restrict__ img, int N, int H, int W, const floa
 // compute_input (detection.py:34-42) into a 16-channel fp16 image (r, g, b, 0 x 13): the A operand of
 // the tensor-core stem convolution (3x3, 16 -> 64 with the 13 padding channels weighted 0).
 __global__ void normalize16_kernel(const uint8_t* __restrict__ img, long long total, __half* __restrict__ out) {
-  // a uint8 input has 256 possible results per channel: the fp64 arithmetic of compute_input runs once per table
-  // entry and block instead of three fp64 divisions per pixel (same expression, same bits)
-  __shared__ __half lut[3][256];
-  const double mean[3] = {0.485 * 255, 0.456 * 255, 0.406 * 255};
-  const double stdv[3] = {0.229 * 255, 0.224 * 255, 0.225 * 255};
-  for (int i = threadIdx.x; i < 3 * 256; i += blockDim.x) {
-    const int c = i >> 8;
-    const float t = static_cast<float>(static_cast<double>(i & 255) - mean[c]);
-    lut[c][i & 255] = __float2half_rn(static_cast<float>(static_cast<double>(t) / stdv[c]));
-  }
-  __syncthreads();
   const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= total) return;
+  const double mean[3] = {0.485 * 255, 0.456 * 255, 0.406 * 255};
+  const double stdv[3] = {0.229 * 255, 0.224 * 255, 0.225 * 255};
   const uint8_t* ip = img + p * 3;
-  const __half2 rg = __halves2half2(lut[0][ip[0]], lut[1][ip[1]]);
-  const __half2 b0 = __halves2half2(lut[2][ip[2]], __float2half_rn(0.0f));
+  float v[3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float t = static_cast<float>(static_cast<double>(ip[c]) - mean[c]);
+    v[c] = static_cast<float>(static_cast<double>(t) / stdv[c]);
+  }
+  const __half2 rg = __floats2half2_rn(v[0], v[1]), b0 = __floats2half2_rn(v[2], 0.0f);
   uint4 lo, hi = make_uint4(0u, 0u, 0u, 0u);
   lo.x = *reinterpret_cast<const uint32_t*>(&rg);
   lo.y = *reinterpret_cast<const uint32_t*>(&b0);
