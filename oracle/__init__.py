@@ -19,9 +19,17 @@ Pinning status ("Oracle"):
 * getBoxes / warpBox /
   resize / pad / inputs  -- pinned: equal to the lifted reference functions
                             (same OpenCV 4.13) on the golden cases.
-* CRNN + STN + CTC       -- PARITY UNPINNED against TensorFlow: TensorFlow is
-                            not installable here, so the restatement follows
-                            the Keras semantics documented in SURVEY.md App. B.
+* CRNN + STN + CTC       -- PARTLY pinned.  TensorFlow is not installable here, but
+                            the reference's own source of ``build_model``,
+                            ``_transform`` and ``CTCDecoder`` (recognition.py:54-350)
+                            is executed on ``oracle/keras_shim.py`` (numpy ``tf`` ops,
+                            torch-backed Keras layers): graph wiring, the STN sampler
+                            line by line and the CTC padding equal the restatement
+                            (softmax to 4e-7, labels identical; tests/golden/crnn.npz).
+                            The arithmetic INSIDE each Keras layer (Conv2D, BN eps 1e-3,
+                            LSTM gates i,f,c,o, greedy ctc_decode) follows the Keras
+                            documentation and stays UNPINNED
+                            against TensorFlow's kernels.
 * shapely                -- absent; ``minimum_rotated_rectangle`` is restated
                             as identity on 4-corner rectangles (the reference's
                             own AttributeError fallback, tools.py:548-550).

@@ -1,11 +1,13 @@
 """Oracle: CRNN recognizer (conv stack + STN + BiLSTM + greedy CTC), fp32 on the CPU.
 
-TEST INFRASTRUCTURE (see oracle/__init__.py).  PARITY UNPINNED against TensorFlow
-(not installable here): this restates ``build_model`` (reference
-keras_ocr/recognition.py:187-350) using the Keras semantics listed in SURVEY.md
-Appendix B (LSTM gate order i,f,c,o with sigmoid/tanh; ``go_backwards`` outputs
-kept in processing order; BatchNormalization eps=1e-3; greedy CTC with repeat
-merging, blank = last class, -1 padding).
+TEST INFRASTRUCTURE (see oracle/__init__.py).  Pinning: the graph wiring, the STN sampler and the
+CTC padding are checked against the reference's OWN source (``build_model``, ``_transform``,
+``CTCDecoder``; recognition.py:54-350) executed on ``oracle/keras_shim.py`` by
+``oracle/validate_against_reference.py`` (softmax equal to 4e-7, labels identical; fixture
+tests/golden/crnn.npz).  PARITY UNPINNED against TensorFlow's kernels (not installable here): the
+arithmetic inside each layer follows the Keras semantics listed in SURVEY.md Appendix B (LSTM gate
+order i,f,c,o with sigmoid/tanh; ``go_backwards`` outputs kept in processing order;
+BatchNormalization eps=1e-3; greedy CTC with repeat merging, blank = last class, -1 padding).
 
 Weights: flat dict with Keras-style names and Keras layouts
   conv_N.kernel (kh,kw,cin,cout), conv_N.bias, bn_N.{gamma,beta,moving_mean,moving_variance},

@@ -178,17 +178,77 @@ def check_inputs(tools, out):
     assert np.array_equal(tools.adjust_boxes(boxes=boxes, boxes_format="boxes", scale=0.5), boxes * 0.5)
 
 
+def check_crnn(out):
+    """The recognizer: the reference's own ``build_model`` / ``_transform`` / ``CTCDecoder`` source
+    (recognition.py:54-350) executed on ``oracle/keras_shim.py`` (numpy ``tf`` ops, torch-backed Keras layers)
+    against ``oracle/crnn.py``.  Pins the graph wiring, the STN sampler line by line and the CTC padding; the
+    per-layer arithmetic is the documented Keras semantics (TensorFlow itself is not installable here)."""
+    from oracle import crnn as o_crnn, keras_shim as shim
+
+    path = os.path.join(REF, "keras_ocr", "recognition.py")
+    with open(path) as f:
+        tree = ast.parse(f.read())
+    params = next(ast.literal_eval(n.value) for n in tree.body if isinstance(n, ast.Assign)
+                  and getattr(n.targets[0], "id", "") == "DEFAULT_BUILD_PARAMS")
+    scope = lift(path, ["_repeat", "_meshgrid", "_transform", "CTCDecoder", "build_model"],
+                 {"tf": shim.tf, "keras": shim.keras, "np": np})
+    alphabet = "0123456789abcdefghijklmnopqrstuvwxyz"
+    shim.reset()
+    backbone, model, training_model, prediction_model = scope["build_model"](alphabet=alphabet, **params)
+    wts = W.synthetic_crnn_weights(seed=2)
+    used = shim.load_weights(wts)
+    assert used == set(wts), sorted(set(wts) - used)          # every tensor found its layer, by the reference's names
+
+    # (1) the STN sampler alone, on transforms far from the identity (clipping quirks exercised)
+    rng = np.random.default_rng(7)
+    feat = rng.standard_normal((3, 50, 7, 8)).astype(np.float32)
+    theta = np.array([[1, 0, 0, 0, 1, 0], [0.8, 0.15, 0.1, -0.1, 1.1, -0.05], [1.3, -0.2, 0.4, 0.25, 0.7, 0.3]], np.float32)
+    ref = scope["_transform"]([feat, theta])
+    mine = o_crnn.stn_sample(torch.from_numpy(feat), torch.from_numpy(theta)).numpy()
+    err = float(np.abs(ref - mine).max())
+    print(f"  _transform (reference source on the numpy shim) vs oracle.stn_sample: max|diff| = {err:.2e}")
+    assert err < 1e-4, err             # coordinates reach 50 in float32: one ulp of the grid moves a sample by ~4e-6
+    assert np.abs(ref[0, -1]).max() < 1e-5 and np.abs(ref[0, :, -1]).max() < 1e-5   # identity theta: last row / column cancel to 0
+    out["stn_features"], out["stn_theta"], out["stn_out"] = feat, theta, ref.astype(np.float32)
+
+    # (2) the whole recognizer on rendered word crops + noise crops
+    gray = synth.noise_gray(rng, 31, 200 * 3)
+    crops = np.stack([gray[:, i * 200:(i + 1) * 200] for i in range(3)])
+    words, _ = synth.text_images(seed=9, n=1, h=62, w=400, n_words=2)
+    word_crop = cv2.resize(cv2.cvtColor(words[0], cv2.COLOR_RGB2GRAY), (200, 31))
+    crops = np.concatenate([crops, word_crop[None]]).astype(np.uint8)
+    x = (crops.astype("float32") / 255)[..., np.newaxis]                  # recognition.py:524-526
+    probs_ref = model.predict(x).numpy()
+    labels_ref = prediction_model.predict(x).numpy()
+    feats_ref = backbone.predict(x).numpy()
+    probs, taps = o_crnn.crnn_logits(wts, x, return_intermediates=True)
+    labels = o_crnn.ctc_greedy(probs)
+    e_l2 = float((taps["l2"] - torch.from_numpy(feats_ref)).abs().max())
+    e_p = float((probs - torch.from_numpy(probs_ref)).abs().max())
+    print(f"  build_model (reference source on the shim) vs oracle: backbone max|diff| = {e_l2:.2e}, softmax {e_p:.2e}, "
+          f"labels equal: {np.array_equal(labels, labels_ref)}")
+    assert probs_ref.shape == (4, 48, 37) and labels_ref.shape == (4, 48)
+    assert e_l2 < 1e-4 and e_p < 1e-4, (e_l2, e_p)
+    assert np.array_equal(labels, labels_ref)
+    out["crnn_crops"] = crops
+    out["crnn_probs"] = probs_ref.astype(np.float32)
+    out["crnn_labels"] = labels_ref.astype(np.int64)
+
+
 def main():
     assert os.path.isdir(REF), f"reference not found at {REF}"
     os.makedirs(GOLDEN, exist_ok=True)
     tools = reference_tools()
     det = reference_detection(tools)
     groups = {}
+    only = set(sys.argv[1:])                             # e.g. `validate_against_reference.py crnn`
     for name, fn, arg in [("craft", check_craft, det), ("boxes", check_boxes, det),
-                          ("warp", check_warp, tools), ("inputs", check_inputs, tools)]:
+                          ("warp", check_warp, tools), ("inputs", check_inputs, tools), ("crnn", check_crnn, None)]:
+        if only and name not in only:
+            continue
         print(f"[{name}]")
         out = {}
-        fn(arg, out)
+        fn(*([arg, out] if arg is not None else [out]))
         groups[name] = out
     for name, out in groups.items():
         path = os.path.join(GOLDEN, f"{name}.npz")

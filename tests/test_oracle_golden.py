@@ -91,3 +91,35 @@ def test_stn_sampler_quirk_zero_last_row_and_column():
     out = crnn.stn_sample(feat, theta)
     assert float(out[0, :, 6].abs().max()) == 0.0 and float(out[0, 49].abs().max()) == 0.0
     np.testing.assert_allclose(out[0, :49, :6].numpy(), 1.0, atol=1e-6)
+
+
+def test_crnn_matches_reference_source_on_the_keras_shim(golden_dir):
+    """tests/golden/crnn.npz = outputs of the reference's OWN ``build_model`` / ``_transform`` / ``CTCDecoder`` source
+    (recognition.py:54-350) executed on oracle/keras_shim.py (written by oracle/validate_against_reference.py).
+    Pins the recognizer's wiring, the STN sampler and the CTC padding of the oracle; the per-layer arithmetic is the
+    documented Keras semantics (TensorFlow is not installable offline)."""
+    g = np.load(os.path.join(golden_dir, "crnn.npz"))
+    wts = W.synthetic_crnn_weights(seed=2)
+    out = crnn.stn_sample(torch.from_numpy(g["stn_features"]), torch.from_numpy(g["stn_theta"]))
+    assert float(np.abs(out.numpy() - g["stn_out"]).max()) < 1e-4
+    with torch.no_grad():
+        probs = crnn.crnn_logits(wts, g["crnn_crops"].astype(np.float32) / 255)
+    assert probs.shape == g["crnn_probs"].shape == (4, 48, 37)
+    assert float(np.abs(probs.numpy() - g["crnn_probs"]).max()) < 1e-4
+    assert np.array_equal(crnn.ctc_greedy(probs), g["crnn_labels"])
+    assert (g["crnn_labels"] >= 0).any()                              # the fixture really decodes characters
+
+
+def test_keras_shim_lstm_is_independent_of_the_oracle_loop():
+    """The shim evaluates LSTM layers with torch.nn.LSTM; the oracle with an explicit gate loop.  Same numbers, both
+    directions, so the gate order [i, f, c, o] / single bias / reversed-output conventions are cross-checked."""
+    from oracle import keras_shim as shim
+    wts = W.synthetic_crnn_weights(seed=4)
+    x = torch.from_numpy(np.random.default_rng(1).standard_normal((2, 50, 128)).astype(np.float32))
+    for name, backwards in (("lstm_10", False), ("lstm_10_back", True)):
+        layer = shim.LSTM(128, go_backwards=backwards, return_sequences=True, name=name)
+        layer.weights = {k: wts[f"{name}.{k}"] for k in ("kernel", "recurrent_kernel", "bias")}
+        with torch.no_grad():
+            ref = layer.forward(x)
+            mine = crnn.lstm(crnn._t(wts), x, name, go_backwards=backwards)
+        assert float((ref - mine).abs().max()) < 1e-5
