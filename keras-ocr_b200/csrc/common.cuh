@@ -7,6 +7,7 @@
 #include <stdio.h>
 
 #include <map>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -51,6 +52,8 @@ struct ConvLayer {
   float* w_f32 = nullptr;      // [taps][cin][cout] fp32 (only for the 3-channel / 1-channel stems)
   float *s1 = nullptr, *t1 = nullptr, *s2 = nullptr, *t2 = nullptr;
   CUtensorMap wmap;            // TMA map over w_kmajor (box 64 x block_n)
+  CUtensorMap wmap_pair;       // the same with box 64 x block_n/2: one CTA's half of a B tile (cta_group::2)
+  bool pair_ok = false;        // wmap_pair is valid (64-channel chunks, block_n >= 64)
   int block_n = 0;             // tcgen05 N tile; 0 = layer not eligible for the tensor-core engine
   int kch = 0;                 // tcgen05 K chunk (channels per stage): 64 / 32 / 16
 };
@@ -66,6 +69,8 @@ struct b2o_ctx {
   int sm_count = 148;
   int conv_engine = B2O_CONV_AUTO;
   int tc_issuers = 0;          // MMA-issuing warps of conv_tc_kernel: 0 = auto (2 for N <= 128 tiles), 1, 2
+  bool tc_pair = false;        // B2O_TC_PAIR=1: CTA pairs (tcgen05 cta_group::2) for the halo-tile layers
+  std::set<const void*> configured;   // kernels whose per-device launch attributes are set on this device
   int64_t launches = 0;
   std::string error;
   std::map<std::string, ConvLayer> craft, crnn;

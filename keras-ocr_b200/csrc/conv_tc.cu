@@ -133,6 +133,40 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar,
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// ---- CTA pairs (cta_group::2).  The two CTAs of a cluster sit on the two SMs of a TPC; in the shared::cluster
+// window the CTA rank is bit 24 of a shared-memory address, so clearing it turns the address of a local
+// barrier into the address of the same barrier in the pair's leader (even) CTA.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA loads of a CTA pair: the data lands in THIS CTA's shared memory, the transaction bytes are counted on the
+// LEADER's barrier (which expects both CTAs' bytes).
+__device__ __forceinline__ void tma_load_4d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1,
+                                                 int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+// one arrival on the leader CTA's copy of `bar` (accumulator stage drained, from either CTA of the pair)
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
+}
 // K-major swizzled shared-memory matrix descriptor: rows of KCH*2 bytes, 8-row atoms SBO bytes apart.
 template <int KCH>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
@@ -158,6 +192,36 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// CTA pair: M = 256 (128 rows from each CTA's A tile), B = BLOCK_N/2 rows from each CTA, accumulators in both
+// CTAs' TMEM at the same columns.  Issued by the leader CTA only.
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// ... and its commit arrives on the barrier at the same offset in BOTH CTAs (mask 0b11)
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(mask)
+               : "memory");
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_issue(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  if (PAIR) umma_f16_pair(tmem_d, adesc, bdesc, idesc, accumulate);
+  else umma_f16(tmem_d, adesc, bdesc, idesc, accumulate);
+}
+template <bool PAIR>
+__device__ __forceinline__ void umma_done(uint64_t* bar) {
+  if (PAIR) umma_commit_pair(bar);
+  else umma_commit(bar);
 }
 template <int CH>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, uint32_t* v);
@@ -198,7 +262,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
-// Walks this CTA's tiles (blockIdx.x, +gridDim.x, ...) keeping the mixed-radix coordinate
+// Walks this CTA's tiles (cta, cta + ncta, ...) keeping the mixed-radix coordinate
 // (n_tile, tile_w, tile_h, tile_n) incrementally: no integer divisions in the per-tile path.
 struct TileIter {
   int c0, c1, c2, c3;        // n_tile, tile_w, tile_h, tile_n
@@ -206,10 +270,11 @@ struct TileIter {
   int r0, r1, r2;            // radices: n_tiles, tiles_w, tiles_h
   int tile, step, total;
   // the CTA's tiles are blockIdx.x + i * gridDim.x; this iterator visits i = first, first + mult, ...
-  __device__ __forceinline__ TileIter(const TcParams& p, int first = 0, int mult = 1) {
+  // cta / ncta: this CTA's (or CTA pair's) index and their number -- blockIdx.x / gridDim.x, halved for pairs
+  __device__ __forceinline__ TileIter(const TcParams& p, int cta, int ncta, int first = 0, int mult = 1) {
     r0 = p.n_tiles; r1 = p.tiles_w; r2 = p.tiles_h;
-    total = p.total_tiles; step = static_cast<int>(gridDim.x) * mult;
-    tile = static_cast<int>(blockIdx.x) + first * static_cast<int>(gridDim.x);
+    total = p.total_tiles; step = ncta * mult;
+    tile = cta + first * ncta;
     int t = tile;
     c0 = t % r0; t /= r0; c1 = t % r1; t /= r1; c2 = t % r2; c3 = t / r2;
     t = step;
@@ -271,11 +336,22 @@ __device__ __forceinline__ void epi_pool8(uint32_t* pk) {
 
 // MODE: 0 = generic tiles, 1 = halo tiles (3x3, dilation 1), 2 = halo tiles + resident filter bank,
 //       3 = as 2 with all A stages of a tile on ONE mbarrier (one wait + one issue region per tile)
-template <int BLOCK_N, int KCH, int MODE>
+// PAIR: clusters of two CTAs (one TPC) run tcgen05.mma.cta_group::2 with M = 256: the CTAs take horizontally
+//       adjacent 8 x 16 pixel tiles (rank = which), each stages its own A boxes and HALF of the B tile
+//       (BLOCK_N / 2 filter rows), the leader CTA issues every MMA for both, each CTA's epilogue drains its own
+//       TMEM.  Per MMA a CTA's shared memory then supplies 4 KB of A + 16*BLOCK_N B of B instead of 32*BLOCK_N,
+//       and the filter bank is fetched from L2 once per 256 pixels instead of once per 128.  Halo modes only.
+template <int BLOCK_N, int KCH, int MODE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                const TcParams p) {
-  constexpr int B_BYTES = BLOCK_N * KCH * 2;
+  static_assert(!PAIR || MODE >= 1, "CTA pairs are implemented for the halo modes");
+  constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // filter rows staged by one CTA
+  constexpr int B_BYTES = B_ROWS * KCH * 2;
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader
+  const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int pair_shift = PAIR ? 1 : 0;                     // tile column = (pair column << 1) + rank
   constexpr int TAP_SHIFT = 16 * KCH;                      // bytes of one 8-pixel row group (= SBO)
   constexpr int KSTEPS = KCH / UMMA_K;
   // TMEM accumulator stages: as many as fit in the 512 columns (max 8).  With only two, a short-K tile is
@@ -330,20 +406,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&tmem_full[s], 1);                          // the commit of the warp that issued the tile
-      mbar_init(&tmem_empty[s], TILE_PAR ? 4 : EPI_THREADS / 32);   // one arrival per epilogue warp on the tile
+      mbar_init(&tmem_empty[s], (PAIR ? 2 : 1) * (TILE_PAR ? 4 : EPI_THREADS / 32));   // one arrival per epilogue warp on the tile (both CTAs of a pair arrive on the leader's)
       mbar_init(&order_bar[s], 1);
     }
     mbar_init(res_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {                                            // the same warp of both CTAs, collectively
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tcgen05_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();                            // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tcgen05_after_sync();
   // Every launch requests > 114 KB of shared memory, so this CTA owns the SM and its TMEM allocation
   // starts at column 0.  Using the literal 0 keeps the accumulator address in a uniform register:
@@ -364,24 +448,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      if (RESIDENT) {                                      // whole filter bank, once per CTA
-        mbar_expect_tx(res_full, static_cast<uint32_t>(taps * kchunks * B_BYTES));
+      const int b_row0 = static_cast<int>(rank) * B_ROWS;  // pair: this CTA's half of the filter rows of an n-tile
+      if (RESIDENT) {                                      // whole filter bank (pair: this CTA's half), once per CTA
+        if (rank == 0) mbar_expect_tx(res_full, static_cast<uint32_t>((PAIR ? 2 : 1) * taps * kchunks * B_BYTES));
         for (int tap = 0; tap < taps; ++tap)
-          for (int kc = 0; kc < kchunks; ++kc)
-            tma_load_2d(&bmap, res_full, smem_b + (tap * kchunks + kc) * B_BYTES, tap * p.cin + kc * KCH, 0);
+          for (int kc = 0; kc < kchunks; ++kc) {
+            if (PAIR) tma_load_2d_pair(&bmap, res_full, smem_b + (tap * kchunks + kc) * B_BYTES, tap * p.cin + kc * KCH, b_row0);
+            else tma_load_2d(&bmap, res_full, smem_b + (tap * kchunks + kc) * B_BYTES, tap * p.cin + kc * KCH, 0);
+          }
       }
       int sa = 0, sb = 0;
       uint32_t pa = 0, pb = 0;
       const int groups = HALO ? 3 : taps;                  // dx positions (halo) or filter taps (generic)
-      for (TileIter ti(p); ti.valid(); ti.next()) {
-        const int tw0 = ti.c1 << p.bw_log2, th0 = ti.c2 << p.bh_log2, tn0 = ti.c3 << p.bn_log2, t_ntile = ti.c0;
+      // pair: the leader's full barriers expect both CTAs' bytes; the peer only issues its loads (onto the
+      // leader's barriers).  The empty barriers are local: the leader's commits arrive on both CTAs' copies.
+      constexpr uint32_t TX_MULT = PAIR ? 2u : 1u;
+      for (TileIter ti(p, cta, ncta); ti.valid(); ti.next()) {
+        const int tw0 = ((ti.c1 << pair_shift) + static_cast<int>(rank)) << p.bw_log2, th0 = ti.c2 << p.bh_log2,
+                  tn0 = ti.c3 << p.bn_log2, t_ntile = ti.c0;
         if (GROUPED) {                                     // every A box of the tile lands on one barrier
           mbar_wait(&a_empty[sa], pa ^ 1);
-          mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(p.group * p.a_bytes));
+          if (rank == 0) mbar_expect_tx(&a_full[sa], TX_MULT * static_cast<uint32_t>(p.group * p.a_bytes));
           uint8_t* dst = smem_a + sa * p.group * p.a_stride;
           for (int g = 0; g < 3; ++g)
             for (int kc = 0; kc < kchunks; ++kc) {
-              tma_load_4d(&amap, &a_full[sa], dst, kc * KCH, tw0 + g - 1, th0 - 1, tn0);
+              if (PAIR) tma_load_4d_pair(&amap, &a_full[sa], dst, kc * KCH, tw0 + g - 1, th0 - 1, tn0);
+              else tma_load_4d(&amap, &a_full[sa], dst, kc * KCH, tw0 + g - 1, th0 - 1, tn0);
               dst += p.a_stride;
             }
           if (++sa == p.na) { sa = 0; pa ^= 1; }
@@ -393,16 +485,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
           const int ay = HALO ? (th0 - 1) : (th0 + (ky - half_k) * p.dil);
           for (int kc = 0; kc < kchunks; ++kc) {
             mbar_wait(&a_empty[sa], pa ^ 1);
-            mbar_expect_tx(&a_full[sa], static_cast<uint32_t>(p.a_bytes));
-            tma_load_4d(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tn0);
+            if (rank == 0) mbar_expect_tx(&a_full[sa], TX_MULT * static_cast<uint32_t>(p.a_bytes));
+            if (PAIR) tma_load_4d_pair(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tn0);
+            else tma_load_4d(&amap, &a_full[sa], smem_a + sa * p.a_stride, kc * KCH, ax, ay, tn0);
             if (++sa == p.na) { sa = 0; pa ^= 1; }
             if (!RESIDENT) {
 #pragma unroll
               for (int t = 0; t < TAPS_PER_A; ++t) {
                 const int tap = HALO ? (t * 3 + g) : g;
                 mbar_wait(&b_empty[sb], pb ^ 1);
-                mbar_expect_tx(&b_full[sb], B_BYTES);
-                tma_load_2d(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, t_ntile * BLOCK_N);
+                if (rank == 0) mbar_expect_tx(&b_full[sb], TX_MULT * B_BYTES);
+                if (PAIR) tma_load_2d_pair(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, t_ntile * BLOCK_N + b_row0);
+                else tma_load_2d(&bmap, &b_full[sb], smem_b + sb * B_BYTES, tap * p.cin + kc * KCH, t_ntile * BLOCK_N);
                 if (++sb == p.nb) { sb = 0; pb ^= 1; }
               }
             }
@@ -412,7 +506,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       }
     }
   } else if (warp >= 1 && warp <= MAX_ISSUERS) {
-    if (warp <= p.issuers) {
+    if (warp <= p.issuers && rank == 0) {                  // pair: the leader issues for both CTAs
     // ===================================================================== MMA issuer
     // The tensor pipe accepts MMAs with (almost) no queue, so every scalar instruction between two
     // UTCHMMAs is exposed.  The issuing warp therefore runs warp-converged (descriptors, stage indices
@@ -420,7 +514,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     // one elected lane) and issues all MMAs of an A stage from ONE elected region where it can.
     // (The code is written for NUM_ISSUERS warps taking alternate A stages; see the note at NUM_ISSUERS.)
     constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
-                               (static_cast<uint32_t>(BLOCK_M >> 4) << 24);   // D=f32, A=B=f16 K-major, N, M=128
+                               (static_cast<uint32_t>((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);   // D=f32, A=B=f16 K-major, N, M=128 (256 per pair)
     constexpr uint32_t TAP_DESC = TAP_SHIFT >> 4, B_DESC = B_BYTES >> 4;       // in 16-byte descriptor units
     const int me = warp - 1;
     const uint64_t a_desc0 = umma_desc<KCH>(smem_u32(smem_a));
@@ -445,7 +539,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
 #else
 #define B2O_TIMED_WAIT(counter, stmt) { stmt; }
 #endif
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tile_seq) {
+    for (int tile = cta; tile < p.total_tiles; tile += ncta, ++tile_seq) {
       if (alternate && (tile_seq & 1) != me) {             // the other warp's tile
         sa += a_per_tile;
         while (sa >= p.na) { sa -= p.na; pa ^= 1; }
@@ -475,15 +569,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                 const uint64_t bdesc = b_desc0 + static_cast<uint64_t>(static_cast<uint32_t>((t * 3 + g) * kchunks + kc) * B_DESC);
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k) {
-                  umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
+                  umma_issue<PAIR>(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k), idesc,
                            accumulate);
                   accumulate = 1;
                 }
               }
               adesc += a_step;
             }
-          umma_commit(&a_empty[sa]);
-          umma_commit(&tmem_full[acc]);
+          umma_done<PAIR>(&a_empty[sa]);
+          umma_done<PAIR>(&tmem_full[acc]);
         }
         __syncwarp();
         if (++sa == p.na) { sa = 0; pa ^= 1; }
@@ -511,11 +605,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
                   // dy tap t = the stage shifted by t rows of 8 pixels; k-step = +32 B inside the swizzle atom
-                  umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc[t] + static_cast<uint64_t>(2 * k),
+                  umma_issue<PAIR>(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc[t] + static_cast<uint64_t>(2 * k),
                            idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
               }
-              if (!RESIDENT) umma_commit(&b_empty[sb]);
-              umma_commit(&a_empty[sa]);                   // frees the A slot when these MMAs retire
+              if (!RESIDENT) umma_done<PAIR>(&b_empty[sb]);
+              umma_done<PAIR>(&a_empty[sa]);                   // frees the A slot when these MMAs retire
             }
             __syncwarp();
             if (!RESIDENT) { if (++sb == p.nb) { sb = 0; pb ^= 1; } }
@@ -530,10 +624,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
               if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < KSTEPS; ++k)
-                  umma_f16(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k),
+                  umma_issue<PAIR>(d_tmem, adesc + static_cast<uint64_t>(t * TAP_DESC + 2 * k), bdesc + static_cast<uint64_t>(2 * k),
                            idesc, (t == 0 && k == 0 && zeroing) ? 0u : 1u);
-                umma_commit(&b_empty[sb]);
-                if (t == TAPS_PER_A - 1) umma_commit(&a_empty[sa]);
+                umma_done<PAIR>(&b_empty[sb]);
+                if (t == TAPS_PER_A - 1) umma_done<PAIR>(&a_empty[sa]);
               }
               __syncwarp();
               if (++sb == p.nb) { sb = 0; pb ^= 1; }
@@ -542,13 +636,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
           if (++sa == p.na) { sa = 0; pa ^= 1; }
         }
       }
-      if (elect_one()) umma_commit(&tmem_full[acc]);
+      if (elect_one()) umma_done<PAIR>(&tmem_full[acc]);
       __syncwarp();
       if (++acc == ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
 #ifdef B2O_TC_DEBUG
-    if (lane == 0 && blockIdx.x < 160 && me == 0) {
-      unsigned long long* d = g_tc_debug + blockIdx.x * 8;
+    if (lane == 0 && cta < 160 && me == 0) {
+      unsigned long long* d = g_tc_debug + cta * 8;
       d[0] = static_cast<unsigned long long>(clock64() - dbg_start);
       d[1] = dbg_t; d[2] = dbg_a; d[3] = dbg_b; d[4] = dbg_tiles;
     }
@@ -568,8 +662,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     constexpr int ACC_STEP = TILE_PAR ? 4 : 1;
     int acc = TILE_PAR ? (sub % ACC_STAGES) : 0;
     uint32_t acc_phase = 0;
-    for (TileIter ti(p, TILE_PAR ? sub : 0, ACC_STEP); ti.valid(); ti.next()) {
-      const int w = (ti.c1 << p.bw_log2) + wi, h = (ti.c2 << p.bh_log2) + hi, n = (ti.c3 << p.bn_log2) + ni;
+    for (TileIter ti(p, cta, ncta, TILE_PAR ? sub : 0, ACC_STEP); ti.valid(); ti.next()) {
+      const int w = (((ti.c1 << pair_shift) + static_cast<int>(rank)) << p.bw_log2) + wi, h = (ti.c2 << p.bh_log2) + hi,
+                n = (ti.c3 << p.bn_log2) + ni;
       const bool valid = (w < p.W) && (h < p.H) && (n < p.N);
       const size_t pix = (static_cast<size_t>(n) * p.H + h) * p.W + w;
       const int c_base = ti.c0 * BLOCK_N;
@@ -653,18 +748,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       }
       tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);        // TMEM stage drained (one arrival per warp)
+      if (lane == 0) {                                     // TMEM stage drained (one arrival per warp)
+        if (PAIR) mbar_arrive_leader(&tmem_empty[acc]);    // the issuer of both CTAs' MMAs lives in the leader
+        else mbar_arrive(&tmem_empty[acc]);
+      }
       acc += ACC_STEP;
       if (acc >= ACC_STAGES) { acc -= ACC_STAGES; acc_phase ^= 1; }
     }
   }
 
   tcgen05_before_sync();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();                            // neither CTA leaves while the other may still signal it
+  else __syncthreads();
   if (warp == 1) {
     tcgen05_after_sync();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS)
-                 : "memory");
+    if (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -708,23 +809,40 @@ double pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
   return best_cover;
 }
 
-template <int BLOCK_N, int KCH, int MODE>
+template <int BLOCK_N, int KCH, int MODE, bool PAIR>
 int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, int smem_bytes,
            cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             232448));
-    configured = true;
+  const void* fn = reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>);
+  if (!ctx->configured.count(fn)) {                        // a per-device attribute: remembered per context
+    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    ctx->configured.insert(fn);
   }
-  const int grid = p.total_tiles < ctx->sm_count ? p.total_tiles : ctx->sm_count;
+  // persistent: one CTA per SM; pairs: one cluster of two CTAs per TPC
+  const int units = PAIR ? ctx->sm_count / 2 : ctx->sm_count;
+  const int grid = (p.total_tiles < units ? p.total_tiles : units) * (PAIR ? 2 : 1);
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   if (ctx->profile) {
     B2O_CUDA_CHECK(ctx, cudaEventCreate(&e0));
     B2O_CUDA_CHECK(ctx, cudaEventCreate(&e1));
     B2O_CUDA_CHECK(ctx, cudaEventRecord(e0, st));
   }
-  conv_tc_kernel<BLOCK_N, KCH, MODE><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
+  if (PAIR) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = static_cast<size_t>(smem_bytes);
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    B2O_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>, amap, L.wmap_pair, p));
+  } else {
+    conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
+  }
   B2O_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
     B2O_CUDA_CHECK(ctx, cudaEventRecord(e1, st));
@@ -762,6 +880,19 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
     return B2O_ERR_CUDA;
   }
   L.block_n = bn;
+  // CTA pairs: each CTA stages bn / 2 filter rows of an n-tile (instantiated for 64-channel chunks, bn >= 64)
+  L.pair_ok = false;
+  if (L.kch == 64 && bn >= 64) {
+    cuuint32_t half_box[2] = {static_cast<cuuint32_t>(L.kch), static_cast<cuuint32_t>(bn / 2)};
+    r = enc(&L.wmap_pair, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, L.w_kmajor, dims, strides, half_box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(L.kch), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      ctx->set_error("cuTensorMapEncodeTiled(pair weights " + L.name + ") failed: " + std::to_string(static_cast<int>(r)));
+      return B2O_ERR_CUDA;
+    }
+    L.pair_ok = true;
+  }
   return B2O_OK;
 }
 
@@ -781,7 +912,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   if (!enc) { ctx->set_error("cuTensorMapEncodeTiled entry point not available"); return B2O_ERR_CUDA; }
   const int kch = L.kch, bn = L.block_n;
   const int taps = L.ksize * L.ksize, kchunks = L.cin / kch;
-  const int b_bytes = bn * kch * 2;
+  int b_bytes = bn * kch * 2;
 
   TcParams p;
   memset(&p, 0, sizeof(p));
@@ -800,7 +931,12 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
             (halo_cover <= 1.15 * generic_cover || want_pool)) ? 1 : 0;
   if (want_pool && !p.halo) { ctx->set_error("conv_tc_run: fused pool needs the halo tile (" + L.name + ")"); return B2O_ERR_ARG; }
   if (p.halo) { p.bw_log2 = 3; p.bh_log2 = 4; p.bn_log2 = 0; }
+  // CTA pairs (opt-in, B2O_TC_PAIR=1): halo tiles only; a pair covers two horizontally adjacent tiles, each CTA
+  // stages half of the B tile.  The accumulation order per output is the same as without pairs.
+  const bool pair = ctx->tc_pair && p.halo && L.pair_ok && ctx->conv_engine == B2O_CONV_AUTO;
+  if (pair) b_bytes /= 2;
   p.tiles_w = (in.w + (1 << p.bw_log2) - 1) >> p.bw_log2;
+  if (pair) p.tiles_w = (p.tiles_w + 1) / 2;                // pair columns
   p.tiles_h = (in.h + (1 << p.bh_log2) - 1) >> p.bh_log2;
   p.tiles_n = (in.n + (1 << p.bn_log2) - 1) >> p.bn_log2;
   p.n_tiles = L.cout / bn;
@@ -818,7 +954,9 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   p.a_bytes = p.halo ? 18 * 8 * kch * 2 : 128 * kch * 2;
   p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
   const long long res_bytes = static_cast<long long>(taps) * kchunks * b_bytes;
-  p.resident = (p.halo && p.n_tiles == 1 && res_bytes + 2LL * p.a_stride <= budget && res_bytes <= (1 << 20) - 1) ? 1 : 0;
+  // (the leader's barrier counts both CTAs' halves of a pair: the mbarrier tx-count holds 2^20 - 1 bytes)
+  p.resident = (p.halo && p.n_tiles == 1 && res_bytes + 2LL * p.a_stride <= budget &&
+                res_bytes * (pair ? 2 : 1) <= (1 << 20) - 1) ? 1 : 0;
   if (p.resident) {
     p.na = static_cast<int>((budget - res_bytes) / p.a_stride);
     const int n_a = 3 * kchunks;                           // A stages per tile
@@ -885,12 +1023,20 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
                    std::to_string(static_cast<int>(r)));
     return B2O_ERR_CUDA;
   }
+#define B2O_TC_PAIR_CASE(BN)                                                                  \
+  if (pair && bn == BN) {                                                                     \
+    if (p.resident && p.group) return launch<BN, 64, 3, true>(ctx, amap, L, p, smem_bytes, st); \
+    if (p.resident) return launch<BN, 64, 2, true>(ctx, amap, L, p, smem_bytes, st);          \
+    return launch<BN, 64, 1, true>(ctx, amap, L, p, smem_bytes, st);                          \
+  }
+  B2O_TC_PAIR_CASE(64); B2O_TC_PAIR_CASE(128); B2O_TC_PAIR_CASE(256);
+#undef B2O_TC_PAIR_CASE
 #define B2O_TC_CASE(BN, KC)                                                            \
   if (bn == BN && kch == KC) {                                                         \
-    if (p.resident && p.group) return launch<BN, KC, 3>(ctx, amap, L, p, smem_bytes, st); \
-    if (p.resident) return launch<BN, KC, 2>(ctx, amap, L, p, smem_bytes, st);         \
-    if (p.halo) return launch<BN, KC, 1>(ctx, amap, L, p, smem_bytes, st);             \
-    return launch<BN, KC, 0>(ctx, amap, L, p, smem_bytes, st);                         \
+    if (p.resident && p.group) return launch<BN, KC, 3, false>(ctx, amap, L, p, smem_bytes, st); \
+    if (p.resident) return launch<BN, KC, 2, false>(ctx, amap, L, p, smem_bytes, st);  \
+    if (p.halo) return launch<BN, KC, 1, false>(ctx, amap, L, p, smem_bytes, st);      \
+    return launch<BN, KC, 0, false>(ctx, amap, L, p, smem_bytes, st);                  \
   }
   B2O_TC_CASE(16, 64); B2O_TC_CASE(32, 64); B2O_TC_CASE(64, 64); B2O_TC_CASE(128, 64); B2O_TC_CASE(256, 64);
   B2O_TC_CASE(16, 32); B2O_TC_CASE(32, 32);
