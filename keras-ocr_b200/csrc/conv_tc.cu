@@ -931,8 +931,9 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
             (halo_cover <= 1.15 * generic_cover || want_pool)) ? 1 : 0;
   if (want_pool && !p.halo) { ctx->set_error("conv_tc_run: fused pool needs the halo tile (" + L.name + ")"); return B2O_ERR_ARG; }
   if (p.halo) { p.bw_log2 = 3; p.bh_log2 = 4; p.bn_log2 = 0; }
-  // CTA pairs (opt-in, B2O_TC_PAIR=1): halo tiles only; a pair covers two horizontally adjacent tiles, each CTA
-  // stages half of the B tile.  The accumulation order per output is the same as without pairs.
+  // CTA pairs (B2O_TC_PAIR=0 turns them off): halo tiles only; a pair covers two horizontally adjacent tiles, each
+  // CTA stages half of the B tile.  The accumulation order per output is the same as without pairs, so the results
+  // are bit-identical (tests/test_gpu_parity.py::test_cta_pairs_give_bit_identical_results).
   const bool pair = ctx->tc_pair && p.halo && L.pair_ok && ctx->conv_engine == B2O_CONV_AUTO;
   if (pair) b_bytes /= 2;
   p.tiles_w = (in.w + (1 << p.bw_log2) - 1) >> p.bw_log2;

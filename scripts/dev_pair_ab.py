@@ -1,5 +1,5 @@
-"""Development A/B: CTA pairs (tcgen05 cta_group::2, B2O_TC_PAIR=1 at context creation) against the default
-single-CTA tiles, alternated in ONE process on ONE box.  Prints whether the score maps / labels are bit-identical
+"""Development A/B: CTA pairs (tcgen05 cta_group::2, the default) against single-CTA tiles (B2O_TC_PAIR=0 at context
+creation), alternated in ONE process on ONE box.  Prints whether the score maps / labels are bit-identical
 (the accumulation order per output is the same) and the step / conv-kernel times of both.
 
     python scripts/dev_pair_ab.py            # PAGES=32 by default
@@ -18,10 +18,7 @@ from oracle import synth
 
 
 def make(pair):
-    if pair:
-        os.environ["B2O_TC_PAIR"] = "1"
-    else:
-        os.environ.pop("B2O_TC_PAIR", None)
+    os.environ["B2O_TC_PAIR"] = "1" if pair else "0"
     det = Detector(weights=W.synthetic_craft_weights(3, textlike=True))
     rec = Recognizer(weights=W.synthetic_crnn_weights(2))
     os.environ.pop("B2O_TC_PAIR", None)

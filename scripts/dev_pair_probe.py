@@ -1,5 +1,5 @@
 """Development probe for the CTA-pair (cta_group::2) convolution path: one small convolution per kernel mode through
-b2o_conv2d_test with B2O_TC_PAIR=1, compared with torch; on a mismatch prints WHERE it is wrong (which CTA of the
+b2o_conv2d_test (pairs are the default; B2O_TC_PAIR=0 disables them), compared with torch; on a mismatch prints WHERE it is wrong (which CTA of the
 pair = tile-column parity, which half of the output channels = which CTA's half of B).
 
     B2O_TC_PAIR=1 python scripts/dev_pair_probe.py

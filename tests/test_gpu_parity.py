@@ -643,3 +643,32 @@ def test_crnn_batch256_labels_do_not_depend_on_the_batch(recognizer):
     assert ((lab >= -1) & (lab < 36)).all()
     pad = lab == -1
     assert (pad[:, :-1] <= pad[:, 1:]).all()                        # once padding starts it continues
+
+
+def test_cta_pairs_give_bit_identical_results(cuda_device, monkeypatch):
+    """The CTA-pair convolution path (tcgen05 cta_group::2, the default) and the single-CTA path (B2O_TC_PAIR=0, read at
+    context creation) add every output's terms in the same order: score maps and CRNN logits are bit-identical, for
+    even and odd numbers of tile columns (the odd one leaves the second CTA of the last pair on a dummy tile)."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.recognition import Recognizer
+    cw, rw = W.synthetic_craft_weights(3), W.synthetic_crnn_weights(2)
+
+    def build(pair):
+        monkeypatch.setenv("B2O_TC_PAIR", "1" if pair else "0")
+        det, rec = Detector(weights=cw), Recognizer(weights=rw)
+        rec.keep_workspace = True
+        return det, rec
+
+    (det1, rec1), (det0, rec0) = build(True), build(False)
+    rng = np.random.default_rng(2)
+    for h, w in ((160, 224), (144, 200)):                 # 200 / 8 = 25 tile columns at full resolution
+        img = torch.from_numpy(rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)).to(cuda_device)
+        assert torch.equal(det1.predict_device(img), det0.predict_device(img))
+    crops = torch.from_numpy(rng.integers(0, 256, (9, 31, 200), dtype=np.uint8)).to(cuda_device)
+    logits = []
+    for rec in (rec1, rec0):
+        x = torch.empty((9, 200, 31), dtype=torch.float16, device=cuda_device)
+        rec.ctx.crops_to_input(crops.data_ptr(), 9, x.data_ptr(), _stream())
+        labels = rec.predict_device(x).clone()
+        logits.append((labels, rec.tap("logits", (9, 48, 37), torch.float32).clone()))
+    assert torch.equal(logits[0][0], logits[1][0]) and torch.equal(logits[0][1], logits[1][1])
