@@ -15,7 +15,10 @@ script writes to ``tests/golden/``.
 Pinning status ("Oracle"):
 
 * CRAFT graph            -- pinned: equals the reference's own PyTorch twin
-                            (detection.py:472-644) to 1e-5 on seeded weights.
+                            (detection.py:472-644) to 1e-5 on seeded weights, and the
+                            reference's Keras graph (build_keras_model +
+                            load_torch_weights source, detection.py:65-103, 290-468,
+                            executed on oracle/keras_shim.py) to 1.2e-5.
 * getBoxes / warpBox /
   resize / pad / inputs  -- pinned: equal to the lifted reference functions
                             (same OpenCV 4.13) on the golden cases.

@@ -1,7 +1,9 @@
 """A minimal stand-in for the ``tensorflow`` / ``keras`` API surface that the reference's
-``keras_ocr/recognition.py:54-350`` touches, so that the reference's OWN source of ``build_model``,
-``_transform``, ``_meshgrid``, ``_repeat`` and ``CTCDecoder`` can be executed (AST-lifted at run time
-by ``oracle/validate_against_reference.py``) without TensorFlow.
+``keras_ocr/recognition.py:54-350`` and ``keras_ocr/detection.py:65-103, 290-468`` touch, so that the
+reference's OWN source of ``build_model``, ``_transform``, ``_meshgrid``, ``_repeat``, ``CTCDecoder`` and of the
+Keras CRAFT (``build_keras_model``, ``build_vgg_backbone``, ``make_vgg_block``, ``upconv``, ``UpsampleLike``,
+``load_torch_weights``) can be executed (AST-lifted at run time by ``oracle/validate_against_reference.py``)
+without TensorFlow.
 
 TEST INFRASTRUCTURE (see oracle/__init__.py).  What this pins and what it does not:
 
@@ -66,7 +68,12 @@ class Layer:
 
     def __call__(self, x):
         many = isinstance(x, (list, tuple))
-        return Sym(lambda *vals: self.forward(list(vals) if many else vals[0]), _parents(x), self.name)
+        self.output = Sym(lambda *vals: self.forward(list(vals) if many else vals[0]), _parents(x), self.name)
+        self.output.layer = self
+        return self.output
+
+    def forward(self, x):                          # subclasses written against the Keras API define call()
+        return self.call(x)
 
 
 MODEL_LAYERS = []          # every layer created since the last reset(), in creation order
@@ -116,19 +123,32 @@ class Lambda(Layer):
 
 
 class Conv2D(Layer):
-    def __init__(self, filters, kernel_size, activation=None, padding="valid", name=None):
+    def __init__(self, filters=None, kernel_size=None, strides=1, padding="valid", dilation_rate=1, activation=None,
+                 name=None):
         super().__init__(name)
-        assert padding == "same" and kernel_size[0] == kernel_size[1] and kernel_size[0] % 2 == 1
-        self.k, self.activation = kernel_size[0], activation
+        k = kernel_size if isinstance(kernel_size, int) else kernel_size[0]
+        assert strides in (1, (1, 1)) and k % 2 == 1 and (padding == "same" or k == 1)
+        self.k, self.dil, self.activation = k, dilation_rate, activation
 
-    def forward(self, x):                          # NHWC in, NHWC out; kernel HWIO
+    def set_weights(self, ws):                     # keras order: [kernel (HWIO), bias]
+        self.weights["kernel"], self.weights["bias"] = ws
+
+    def forward(self, x):                          # NHWC in, NHWC out; kernel HWIO; "same" = symmetric pad for odd k
         w = _t(self.weights["kernel"]).permute(3, 2, 0, 1)
-        y = F.conv2d(x.permute(0, 3, 1, 2), w, _t(self.weights["bias"]), padding=self.k // 2)
+        y = F.conv2d(x.permute(0, 3, 1, 2), w, _t(self.weights["bias"]), padding=self.dil * (self.k // 2),
+                     dilation=self.dil)
         return _act(self.activation, y.permute(0, 2, 3, 1).contiguous())
 
 
 class BatchNormalization(Layer):
-    epsilon = 1e-3                                 # keras default
+    def __init__(self, epsilon=1e-3, momentum=0.99, axis=-1, name=None):     # keras default epsilon
+        super().__init__(name)
+        assert axis == -1
+        self.epsilon = epsilon
+
+    def set_weights(self, ws):                     # keras order: [gamma, beta, moving_mean, moving_variance]
+        for key, value in zip(("gamma", "beta", "moving_mean", "moving_variance"), ws):
+            self.weights[key] = value
 
     def forward(self, x):
         w = self.weights
@@ -137,12 +157,25 @@ class BatchNormalization(Layer):
 
 
 class MaxPooling2D(Layer):
-    def __init__(self, pool_size=(2, 2), name=None):
+    def __init__(self, pool_size=(2, 2), strides=None, padding="valid", name=None):
         super().__init__(name)
-        self.pool = tuple(pool_size)
+        pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)      # noqa: E731
+        self.pool = pair(pool_size)
+        self.strides = self.pool if strides is None else pair(strides)   # keras default: strides = pool_size
+        assert padding == "valid" or (self.strides == (1, 1) and self.pool[0] % 2 == 1)
+        self.pad = 0 if padding == "valid" else self.pool[0] // 2        # "same" pads with -inf (ignored by max)
 
-    def forward(self, x):                          # strides = pool_size, padding "valid" (keras defaults)
-        return F.max_pool2d(x.permute(0, 3, 1, 2), self.pool, self.pool).permute(0, 2, 3, 1).contiguous()
+    def forward(self, x):
+        return F.max_pool2d(x.permute(0, 3, 1, 2), self.pool, self.strides, self.pad).permute(0, 2, 3, 1).contiguous()
+
+
+class Activation(Layer):
+    def __init__(self, activation, name=None):
+        super().__init__(name)
+        self.activation = activation
+
+    def forward(self, x):
+        return _act(self.activation, x)
 
 
 class Flatten(Layer):
@@ -212,6 +245,26 @@ class Model:
         self.inputs, self.outputs = inputs, outputs
         self.input, self.output = inputs, outputs
         self.output_shape = (None, None, None)
+
+    @property
+    def layers(self):
+        """Layers on the paths from the inputs to the outputs (what keras.Model.layers holds)."""
+        seen, found, stack = set(), [], _parents(self.outputs)
+        while stack:
+            node = stack.pop()
+            if id(node) in seen:
+                continue
+            seen.add(id(node))
+            if getattr(node, "layer", None) is not None:
+                found.append(node.layer)
+            stack.extend(node.parents)
+        return found[::-1]
+
+    def get_layer(self, name):
+        for layer in self.layers:
+            if layer.name == name:
+                return layer
+        raise ValueError(f"No such layer: {name}")
 
     def __call__(self, x):
         if isinstance(x, Sym):                     # a model used as a layer (the localisation net)
@@ -305,9 +358,20 @@ tf = types.SimpleNamespace(
                                                       constant_values=constant_values),
 )
 
-backend = types.SimpleNamespace(shape=tf.shape, cast=_cast, ctc_decode=_ctc_decode, ctc_batch_cost=lambda **kw: None)
-layers = types.SimpleNamespace(Input=Input, Permute=Permute, Lambda=Lambda, Conv2D=Conv2D,
+def _resize_bilinear(source, size, half_pixel_centers=False):
+    """tf.compat.v1.image.resize_bilinear(half_pixel_centers=True) on NHWC = torch bilinear, align_corners=False."""
+    assert half_pixel_centers
+    x = source if isinstance(source, torch.Tensor) else _t(source)
+    y = F.interpolate(x.permute(0, 3, 1, 2), size=(int(size[0]), int(size[1])), mode="bilinear", align_corners=False)
+    return y.permute(0, 2, 3, 1).contiguous()
+
+
+tf.compat = types.SimpleNamespace(v1=types.SimpleNamespace(image=types.SimpleNamespace(resize_bilinear=_resize_bilinear)))
+backend = types.SimpleNamespace(shape=tf.shape, cast=_cast, ctc_decode=_ctc_decode, ctc_batch_cost=lambda **kw: None,
+                                image_data_format=lambda: "channels_last")
+layers = types.SimpleNamespace(Input=Input, Permute=Permute, Lambda=Lambda, Conv2D=Conv2D, Activation=Activation,
                                BatchNormalization=BatchNormalization, MaxPooling2D=MaxPooling2D, Flatten=Flatten,
-                               Reshape=Reshape, Dense=Dense, LSTM=LSTM, Add=Add, Concatenate=Concatenate, Dropout=Dropout)
+                               Reshape=Reshape, Dense=Dense, LSTM=LSTM, Add=Add, Concatenate=Concatenate, Dropout=Dropout,
+                               Layer=Layer)
 keras = types.SimpleNamespace(layers=layers, models=types.SimpleNamespace(Model=Model), backend=backend)
 tf.keras = keras

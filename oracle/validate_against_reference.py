@@ -31,7 +31,7 @@ def lift(path, names, scope):
     """exec the named top-level functions of ``path`` inside ``scope``."""
     with open(path) as f:
         tree = ast.parse(f.read())
-    wanted = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    wanted = [n for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and n.name in names]
     missing = set(names) - {n.name for n in wanted}
     assert not missing, missing
     mod = ast.Module(body=wanted, type_ignores=[])
@@ -178,6 +178,39 @@ def check_inputs(tools, out):
     assert np.array_equal(tools.adjust_boxes(boxes=boxes, boxes_format="boxes", scale=0.5), boxes * 0.5)
 
 
+def check_craft_keras(out):
+    """The KERAS flavour of CRAFT -- the graph ``Detector()`` builds by default -- from the reference's own source
+    (``build_keras_model`` + ``load_torch_weights``, detection.py:65-103, 290-468) executed on ``oracle/keras_shim.py``,
+    against the oracle and against the torch-twin scores already in craft.npz."""
+    import tempfile
+    from oracle import keras_shim as shim
+
+    scope = lift(os.path.join(REF, "keras_ocr", "detection.py"),
+                 ["upconv", "make_vgg_block", "UpsampleLike", "build_vgg_backbone", "build_keras_model", "load_torch_weights"],
+                 {"tf": shim.tf, "keras": shim.keras, "np": np, "typing": __import__("typing")})
+    wts = W.synthetic_craft_weights(seed=3)
+    state = {"module." + k: torch.from_numpy(np.asarray(v)) for k, v in wts.items()}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "craft_synthetic.pth")
+        torch.save(state, path)
+        shim.reset()
+        model = scope["build_keras_model"](weights_path=path, backbone_name="vgg")
+    golden = np.load(os.path.join(GOLDEN, "craft.npz"))
+    worst = 0.0
+    for tag in ("even", "odd"):
+        img = golden[f"craft_{tag}_image"]
+        x = np.stack([o_img.compute_input(i) for i in img])
+        got = model.predict(x).numpy()
+        with torch.no_grad():
+            mine = o_craft.craft_forward(wts, torch.from_numpy(x).permute(0, 3, 1, 2).contiguous()).numpy()
+        e_oracle = float(np.abs(got - mine).max())
+        e_twin = float(np.abs(got - golden[f"craft_{tag}_scores"]).max())
+        worst = max(worst, e_oracle, e_twin)
+        print(f"  Keras CRAFT (reference source on the shim) {tag}: vs oracle {e_oracle:.2e}, vs the reference's torch twin {e_twin:.2e}")
+        out[f"craft_keras_{tag}_scores"] = got.astype(np.float32)
+    assert worst < 1e-4, worst            # the reference's own Keras-vs-torch bar (tests/test_pytorch_keras.py:49)
+
+
 def check_crnn(out):
     """The recognizer: the reference's own ``build_model`` / ``_transform`` / ``CTCDecoder`` source
     (recognition.py:54-350) executed on ``oracle/keras_shim.py`` (numpy ``tf`` ops, torch-backed Keras layers)
@@ -243,7 +276,8 @@ def main():
     groups = {}
     only = set(sys.argv[1:])                             # e.g. `validate_against_reference.py crnn`
     for name, fn, arg in [("craft", check_craft, det), ("boxes", check_boxes, det),
-                          ("warp", check_warp, tools), ("inputs", check_inputs, tools), ("crnn", check_crnn, None)]:
+                          ("warp", check_warp, tools), ("inputs", check_inputs, tools), ("crnn", check_crnn, None),
+                          ("craft_keras", check_craft_keras, None)]:
         if only and name not in only:
             continue
         print(f"[{name}]")

@@ -123,3 +123,18 @@ def test_keras_shim_lstm_is_independent_of_the_oracle_loop():
             ref = layer.forward(x)
             mine = crnn.lstm(crnn._t(wts), x, name, go_backwards=backwards)
         assert float((ref - mine).abs().max()) < 1e-5
+
+
+def test_craft_matches_reference_keras_source_on_the_shim(golden_dir):
+    """tests/golden/craft_keras.npz = the reference's KERAS CRAFT (``build_keras_model`` + ``load_torch_weights``,
+    detection.py:65-103, 290-468 -- the graph ``Detector()`` builds by default) executed on oracle/keras_shim.py for the
+    images of craft.npz; the oracle and the reference's torch twin both agree with it to the reference's own
+    Keras-vs-torch bar (tests/test_pytorch_keras.py:49: 1e-4)."""
+    g, gk = _load(golden_dir, "craft"), _load(golden_dir, "craft_keras")
+    wts = W.synthetic_craft_weights(seed=3)
+    for tag in ("even", "odd"):
+        x = np.stack([imageops.compute_input(i) for i in g[f"craft_{tag}_image"]])
+        with torch.no_grad():
+            mine = craft.craft_forward(wts, torch.from_numpy(x).permute(0, 3, 1, 2).contiguous()).numpy()
+        assert float(np.abs(mine - gk[f"craft_keras_{tag}_scores"]).max()) < 1e-4
+        assert float(np.abs(g[f"craft_{tag}_scores"] - gk[f"craft_keras_{tag}_scores"]).max()) < 1e-4
