@@ -50,15 +50,24 @@ def unpack_records(rec, max_boxes):
 
 
 def unpack_blocks(blocks, max_boxes):
-    """All gathered blocks at once (rank order = global image order), vectorised: returns (counts (n_images,),
-    boxes (total,4,2) float32, labels (total,48) int8) with the words of image i at [sum(counts[:i]), +counts[i])."""
-    rec = np.concatenate([np.asarray(b.cpu() if isinstance(b, torch.Tensor) else b) for b in blocks], axis=0)
-    rec = rec[rec[:, 0] >= 0]                          # drop the padding rows of short shards
-    counts = rec[:, 0].astype(np.int64)
-    used = np.arange(max_boxes)[None, :] < counts[:, None]
-    boxes = rec[:, 1:1 + max_boxes * 8].reshape(-1, max_boxes, 4, 2)[used]
-    labels = np.ascontiguousarray(rec[:, 1 + max_boxes * 8:]).view(np.int8).reshape(-1, max_boxes, STEPS)[used]
-    return counts, boxes, labels
+    """All gathered blocks at once (rank order = global image order): returns (counts (n_images,), boxes (total,4,2)
+    float32, labels (total,48) int8) with the words of image i at [sum(counts[:i]), +counts[i]).  Only the used
+    prefix of every record is touched (two concatenations of per-image views), not the 75 % padding."""
+    box_parts, lab_parts, counts = [], [], []
+    lab0 = (1 + max_boxes * 8) * 4                     # byte offset of the label area inside a record
+    for block in blocks:
+        rec = np.ascontiguousarray(np.asarray(block.cpu() if isinstance(block, torch.Tensor) else block))
+        rec8 = rec.view(np.int8)
+        for i, c in enumerate(rec[:, 0].astype(np.int64).tolist()):
+            if c < 0:                                  # padding row of a short shard
+                continue
+            counts.append(c)
+            if c:
+                box_parts.append(rec[i, 1:1 + c * 8])
+                lab_parts.append(rec8[i, lab0:lab0 + c * STEPS])
+    boxes = np.concatenate(box_parts).reshape(-1, 4, 2) if box_parts else np.zeros((0, 4, 2), np.float32)
+    labels = np.concatenate(lab_parts).reshape(-1, STEPS) if lab_parts else np.zeros((0, STEPS), np.int8)
+    return np.asarray(counts, dtype=np.int64), boxes, labels
 
 
 def gather_records(local, world_size, rank, device=None):
@@ -124,5 +133,8 @@ def recognize_sharded(pipeline, images, max_boxes=128, presharded=False):
         return None
     counts, boxes, labels = unpack_blocks(blocks, max_boxes)
     texts = recognition.labels_to_text(labels, alphabet)
-    ends = np.cumsum(counts)
-    return [list(zip(texts[e - c:e], boxes[e - c:e])) for c, e in zip(counts, ends)]
+    quads, out, start = list(boxes), [], 0             # one (4,2) view per word, made once
+    for c in counts.tolist():
+        out.append(list(zip(texts[start:start + c], quads[start:start + c])))
+        start += c
+    return out

@@ -14,17 +14,21 @@ TARGET_HEIGHT, TARGET_WIDTH, STEPS = 31, 200, 48                # DEFAULT_BUILD_
 def labels_to_text(rows, alphabet=DEFAULT_ALPHABET):
     """reference recognition.py:527-534: drop blank / -1, map indices to characters.
 
-    The CTC decoder emits the kept labels as a prefix of each row, so the common case is a table
-    lookup plus a NUL-terminated view (no per-character Python loop); any other row layout falls
-    back to the reference's element-wise filter."""
+    Vectorised: the kept labels of all rows are gathered into ONE byte string with a newline after every row, decoded
+    once and split (no per-character and no per-row Python work besides the split); alphabets that are not ASCII or
+    contain a newline, and tables with out-of-range indices, take the reference's element-wise filter."""
     blank = len(alphabet)
     rows = np.asarray(rows)
-    if rows.ndim == 2 and rows.size and alphabet.isascii():
+    if rows.ndim == 2 and rows.size and alphabet.isascii() and "\n" not in alphabet:
         keep = (rows != blank) & (rows != -1)
-        if bool(np.all(keep[:, :-1] >= keep[:, 1:])) and bool(np.all(rows[keep] >= 0)) and bool(np.all(rows[keep] < blank)):
-            lut = np.frombuffer((alphabet + "\0").encode("ascii"), dtype=np.uint8)
-            codes = np.ascontiguousarray(lut[np.where(keep, rows, blank)])
-            return [b.decode("ascii") for b in codes.view(f"S{rows.shape[1]}").ravel().tolist()]
+        flat = rows[keep]
+        if flat.size == 0 or (int(flat.min()) >= 0 and int(flat.max()) < blank):
+            out = np.full(flat.size + rows.shape[0], 10, dtype=np.uint8)          # 10 = "\n"
+            ends = np.cumsum(keep.sum(1) + 1) - 1
+            chars = np.ones(out.size, dtype=bool)
+            chars[ends] = False
+            out[chars] = np.frombuffer(alphabet.encode("ascii"), dtype=np.uint8)[flat]
+            return out.tobytes().decode("ascii").split("\n")[:-1]
     return ["".join(alphabet[idx] for idx in row if idx not in (blank, -1)) for row in rows]
 
 
