@@ -809,6 +809,8 @@ double pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
   return best_cover;
 }
 
+constexpr int kRetrySingle = 1;            // launch(): the pair launch was refused, plan the layer again without pairs
+
 template <int BLOCK_N, int KCH, int MODE, bool PAIR>
 int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, int smem_bytes,
            cudaStream_t st) {
@@ -839,7 +841,16 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    B2O_CUDA_CHECK(ctx, cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>, amap, L.wmap_pair, p));
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>, amap, L.wmap_pair, p);
+    if (le != cudaSuccess) {
+      // a device / partition that cannot co-schedule two such CTAs on a TPC: fall back, once and for good, to the
+      // single-CTA tiles of the same kernel (bit-identical results)
+      cudaGetLastError();
+      if (e0) { cudaEventDestroy(e0); cudaEventDestroy(e1); }
+      fprintf(stderr, "b2ocr: CTA-pair launch failed (%s); using single-CTA convolution tiles\n", cudaGetErrorString(le));
+      ctx->tc_pair = false;
+      return kRetrySingle;
+    }
   } else {
     conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
   }
@@ -1026,9 +1037,10 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   }
 #define B2O_TC_PAIR_CASE(BN)                                                                  \
   if (pair && bn == BN) {                                                                     \
-    if (p.resident && p.group) return launch<BN, 64, 3, true>(ctx, amap, L, p, smem_bytes, st); \
-    if (p.resident) return launch<BN, 64, 2, true>(ctx, amap, L, p, smem_bytes, st);          \
-    return launch<BN, 64, 1, true>(ctx, amap, L, p, smem_bytes, st);                          \
+    const int rc = (p.resident && p.group) ? launch<BN, 64, 3, true>(ctx, amap, L, p, smem_bytes, st) \
+                   : p.resident            ? launch<BN, 64, 2, true>(ctx, amap, L, p, smem_bytes, st) \
+                                           : launch<BN, 64, 1, true>(ctx, amap, L, p, smem_bytes, st); \
+    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full) : rc; \
   }
   B2O_TC_PAIR_CASE(64); B2O_TC_PAIR_CASE(128); B2O_TC_PAIR_CASE(256);
 #undef B2O_TC_PAIR_CASE
