@@ -340,12 +340,13 @@ __device__ __forceinline__ void epi_pool8(uint32_t* pk) {
 //       adjacent 8 x 16 pixel tiles (rank = which), each stages its own A boxes and HALF of the B tile
 //       (BLOCK_N / 2 filter rows), the leader CTA issues every MMA for both, each CTA's epilogue drains its own
 //       TMEM.  Per MMA a CTA's shared memory then supplies 4 KB of A + 16*BLOCK_N B of B instead of 32*BLOCK_N,
-//       and the filter bank is fetched from L2 once per 256 pixels instead of once per 128.  Halo modes only.
+//       and the filter bank is fetched from L2 once per 256 pixels instead of once per 128.  Validated and on by
+//       default for the halo modes; generic tiles (MODE 0: 1x1 and dilated layers) pair the same way but are opt-in
+//       (B2O_TC_PAIR=2) until they have run on a GPU.
 template <int BLOCK_N, int KCH, int MODE, bool PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                const TcParams p) {
-  static_assert(!PAIR || MODE >= 1, "CTA pairs are implemented for the halo modes");
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // filter rows staged by one CTA
   constexpr int B_BYTES = B_ROWS * KCH * 2;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader
@@ -945,7 +946,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   // CTA pairs (B2O_TC_PAIR=0 turns them off): halo tiles only; a pair covers two horizontally adjacent tiles, each
   // CTA stages half of the B tile.  The accumulation order per output is the same as without pairs, so the results
   // are bit-identical (tests/test_gpu_parity.py::test_cta_pairs_give_bit_identical_results).
-  const bool pair = ctx->tc_pair && p.halo && L.pair_ok && ctx->conv_engine == B2O_CONV_AUTO;
+  const bool pair = ctx->tc_pair && (p.halo || ctx->tc_pair_generic) && L.pair_ok && ctx->conv_engine == B2O_CONV_AUTO;
   if (pair) b_bytes /= 2;
   p.tiles_w = (in.w + (1 << p.bw_log2) - 1) >> p.bw_log2;
   if (pair) p.tiles_w = (p.tiles_w + 1) / 2;                // pair columns
@@ -1039,7 +1040,8 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   if (pair && bn == BN) {                                                                     \
     const int rc = (p.resident && p.group) ? launch<BN, 64, 3, true>(ctx, amap, L, p, smem_bytes, st) \
                    : p.resident            ? launch<BN, 64, 2, true>(ctx, amap, L, p, smem_bytes, st) \
-                                           : launch<BN, 64, 1, true>(ctx, amap, L, p, smem_bytes, st); \
+                   : p.halo                ? launch<BN, 64, 1, true>(ctx, amap, L, p, smem_bytes, st) \
+                                           : launch<BN, 64, 0, true>(ctx, amap, L, p, smem_bytes, st); \
     return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full) : rc; \
   }
   B2O_TC_PAIR_CASE(64); B2O_TC_PAIR_CASE(128); B2O_TC_PAIR_CASE(256);
