@@ -189,6 +189,7 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : (atoi(e) == 1 ? 1 : 0);
+  if (const char* e = getenv("B2O_TC_BOX16")) ctx->tc_box16 = atoi(e) != 0;
   if (const char* e = getenv("B2O_TC_PAIR")) {        // default 1; 0 = single-CTA tiles (A/B runs); 2 = generic tiles too
     ctx->tc_pair = atoi(e) != 0;
     ctx->tc_pair_generic = atoi(e) == 2;

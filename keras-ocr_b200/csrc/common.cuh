@@ -70,6 +70,7 @@ struct b2o_ctx {
   int conv_engine = B2O_CONV_AUTO;
   int tc_issuers = 0;          // MMA-issuing warps of conv_tc_kernel: 0 = auto (2 for N <= 128 tiles), 1, 2
   bool tc_pair = true;         // CTA pairs (tcgen05 cta_group::2) for the halo-tile layers; B2O_TC_PAIR=0 turns them off
+  bool tc_box16 = false;       // B2O_TC_BOX16=1: one 16 x 18 A box per K chunk in MODE 3 layers -- not yet GPU-validated
   bool tc_pair_generic = false;   // B2O_TC_PAIR=2: also pair the generic tiles (1x1 / dilated layers) -- not yet GPU-validated
   std::set<const void*> configured;   // kernels whose per-device launch attributes are set on this device
   int64_t launches = 0;

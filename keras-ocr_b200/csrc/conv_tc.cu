@@ -68,6 +68,7 @@ struct TcParams {
   int wide;                 // output rows are 32-byte aligned: one 256-bit store per 16 fp16 channels (full sector)
   __half* pool_out;                       // fused 2x2/2 max-pool output (or null)
   int pool_ld, PH, PW;
+  int box16;                              // MODE 3 with ONE 16 x 18 A box per K chunk (dx taps through the descriptor)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -168,9 +169,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(smem_u32(bar) & PEER_BIT_MASK) : "memory");
 }
 // K-major swizzled shared-memory matrix descriptor: rows of KCH*2 bytes, 8-row atoms SBO bytes apart.
-template <int KCH>
+template <int KCH, int SBO_BYTES = 16 * KCH>
 __device__ __forceinline__ uint64_t umma_desc(uint32_t saddr) {
-  constexpr uint64_t SBO = 16 * KCH;                       // 8 rows x (KCH*2) bytes
+  constexpr uint64_t SBO = SBO_BYTES;                      // 8 rows x (KCH*2) bytes unless the rows are strided apart
   constexpr uint64_t LAYOUT = KCH == 64 ? 2 : (KCH == 32 ? 4 : 6);   // SWIZZLE_128B / 64B / 32B
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);    // start address      bits [0,14)
@@ -343,17 +344,24 @@ __device__ __forceinline__ void epi_pool8(uint32_t* pk) {
 //       and the filter bank is fetched from L2 once per 256 pixels instead of once per 128.  Validated and on by
 //       default for the halo modes; generic tiles (MODE 0: 1x1 and dilated layers) pair the same way but are opt-in
 //       (B2O_TC_PAIR=2) until they have run on a GPU.
-template <int BLOCK_N, int KCH, int MODE, bool PAIR>
+// BOX16 (MODE 3 only, opt-in B2O_TC_BOX16=1, NOT yet validated on a GPU -- scripts/probes/dx_shift_probe.cu tests the
+//       descriptor semantics it relies on): ONE 16 x 18-pixel A box per K chunk serves all nine taps.  The dy taps
+//       move the A descriptor by whole image rows (2 KB = the stride between 8-row groups), the dx taps by single
+//       128-byte pixel rows inside a swizzle atom, with the descriptor's base offset set to dx.  2.25x instead of
+//       3.375x of the tile's input crosses L2->SM, in one TMA instruction instead of three and 36 KB instead of 55 KB.
+//       The MMAs are issued in the same (dx, chunk, dy, k) order as without it.
+template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                const TcParams p) {
+  static_assert(!BOX16 || (MODE == 3 && KCH == 64), "the single-box tile is implemented for grouped tiles, 64-channel chunks");
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // filter rows staged by one CTA
   constexpr int B_BYTES = B_ROWS * KCH * 2;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader
   const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int pair_shift = PAIR ? 1 : 0;                     // tile column = (pair column << 1) + rank
-  constexpr int TAP_SHIFT = 16 * KCH;                      // bytes of one 8-pixel row group (= SBO)
+  constexpr int TAP_SHIFT = (BOX16 ? 32 : 16) * KCH;       // bytes between the tile's image rows in an A stage (= SBO)
   constexpr int KSTEPS = KCH / UMMA_K;
   // TMEM accumulator stages: as many as fit in the 512 columns (max 8).  With only two, a short-K tile is
   // bound by the *latency* of the epilogue hand-off (tmem_full -> LDTM -> stores -> tmem_empty), not by its
@@ -471,7 +479,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
           mbar_wait(&a_empty[sa], pa ^ 1);
           if (rank == 0) mbar_expect_tx(&a_full[sa], TX_MULT * static_cast<uint32_t>(p.group * p.a_bytes));
           uint8_t* dst = smem_a + sa * p.group * p.a_stride;
-          for (int g = 0; g < 3; ++g)
+          for (int g = 0; g < (BOX16 ? 1 : 3); ++g)        // BOX16: one 16-pixel-wide box holds all three dx positions
             for (int kc = 0; kc < kchunks; ++kc) {
               if (PAIR) tma_load_4d_pair(&amap, &a_full[sa], dst, kc * KCH, tw0 + g - 1, th0 - 1, tn0);
               else tma_load_4d(&amap, &a_full[sa], dst, kc * KCH, tw0 + g - 1, th0 - 1, tn0);
@@ -518,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                                (static_cast<uint32_t>((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);   // D=f32, A=B=f16 K-major, N, M=128 (256 per pair)
     constexpr uint32_t TAP_DESC = TAP_SHIFT >> 4, B_DESC = B_BYTES >> 4;       // in 16-byte descriptor units
     const int me = warp - 1;
-    const uint64_t a_desc0 = umma_desc<KCH>(smem_u32(smem_a));
+    const uint64_t a_desc0 = umma_desc<KCH, TAP_SHIFT>(smem_u32(smem_a));
     const uint64_t b_desc0 = umma_desc<KCH>(smem_u32(smem_b));
     const uint32_t a_step = static_cast<uint32_t>(p.a_stride) >> 4;
     if (RESIDENT) { mbar_wait(res_full, 0); tcgen05_after_sync(); }
@@ -563,7 +571,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         if (elect_one()) {
           uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa * p.group) * a_step);
           uint32_t accumulate = 0;
-          for (int g = 0; g < 3; ++g)
+          // BOX16: dx = one 128-byte pixel row further into the same stages, descriptor base offset (bits 49-51) = dx
+          constexpr uint64_t DX_STEP = (static_cast<uint64_t>(1) << 49) | static_cast<uint64_t>((KCH * 2) >> 4);
+          const uint64_t adesc_tile = adesc;
+          for (int g = 0; g < 3; ++g) {
+            if (BOX16) adesc = adesc_tile + static_cast<uint64_t>(g) * DX_STEP;
             for (int kc = 0; kc < kchunks; ++kc) {
 #pragma unroll
               for (int t = 0; t < 3; ++t) {
@@ -577,6 +589,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
               }
               adesc += a_step;
             }
+          }
           umma_done<PAIR>(&a_empty[sa]);
           umma_done<PAIR>(&tmem_full[acc]);
         }
@@ -812,12 +825,12 @@ double pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
 
 constexpr int kRetrySingle = 1;            // launch(): the pair launch was refused, plan the layer again without pairs
 
-template <int BLOCK_N, int KCH, int MODE, bool PAIR>
+template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false>
 int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, int smem_bytes,
            cudaStream_t st) {
-  const void* fn = reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>);
+  const void* fn = reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16>);
   if (!ctx->configured.count(fn)) {                        // a per-device attribute: remembered per context
-    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>,
+    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     ctx->configured.insert(fn);
   }
@@ -842,7 +855,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR>, amap, L.wmap_pair, p);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16>, amap, L.wmap_pair, p);
     if (le != cudaSuccess) {
       // a device / partition that cannot co-schedule two such CTAs on a TPC: fall back, once and for good, to the
       // single-CTA tiles of the same kernel (bit-identical results)
@@ -853,7 +866,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
       return kRetrySingle;
     }
   } else {
-    conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
+    conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
   }
   B2O_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
@@ -970,9 +983,15 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   // (the leader's barrier counts both CTAs' halves of a pair: the mbarrier tx-count holds 2^20 - 1 bytes)
   p.resident = (p.halo && p.n_tiles == 1 && res_bytes + 2LL * p.a_stride <= budget &&
                 res_bytes * (pair ? 2 : 1) <= (1 << 20) - 1) ? 1 : 0;
+  // opt-in (B2O_TC_BOX16=1, not GPU-validated): one 16-pixel-wide box per K chunk instead of three 8-pixel-wide ones,
+  // where the layer then still runs as whole tiles per barrier (MODE 3)
+  if (ctx->tc_box16 && p.resident && kch == 64 && (bn == 64 || bn == 128) && ctx->conv_engine == B2O_CONV_AUTO) {
+    const int a16 = 18 * 16 * kch * 2;                     // 36864 B: a whole number of 1 KB swizzle atoms
+    if ((budget - res_bytes) / a16 >= 2 * kchunks) { p.box16 = 1; p.a_bytes = a16; p.a_stride = a16; }
+  }
   if (p.resident) {
     p.na = static_cast<int>((budget - res_bytes) / p.a_stride);
-    const int n_a = 3 * kchunks;                           // A stages per tile
+    const int n_a = (p.box16 ? 1 : 3) * kchunks;           // A stages per tile
     if (p.na >= 2 * n_a) {                                 // MODE 3: whole tiles per barrier
       p.group = n_a;
       p.na = p.na / n_a;
@@ -1026,7 +1045,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.ld) * 2, static_cast<cuuint64_t>(in.ld) * 2 * in.w,
                            static_cast<cuuint64_t>(in.ld) * 2 * in.w * in.h};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(kch), 1u << p.bw_log2, 1u << p.bh_log2, 1u << p.bn_log2};
-  if (p.halo) { box[1] = 8; box[2] = 18; box[3] = 1; }
+  if (p.halo) { box[1] = p.box16 ? 16 : 8; box[2] = 18; box[3] = 1; }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in.ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kch), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1036,6 +1055,14 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
                    std::to_string(static_cast<int>(r)));
     return B2O_ERR_CUDA;
   }
+#define B2O_TC_BOX16_CASE(BN)                                                                          \
+  if (p.box16 && p.group && bn == BN) {                                                               \
+    const int rc = pair ? launch<BN, 64, 3, true, true>(ctx, amap, L, p, smem_bytes, st)              \
+                        : launch<BN, 64, 3, false, true>(ctx, amap, L, p, smem_bytes, st);            \
+    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full) : rc; \
+  }
+  B2O_TC_BOX16_CASE(64); B2O_TC_BOX16_CASE(128);
+#undef B2O_TC_BOX16_CASE
 #define B2O_TC_PAIR_CASE(BN)                                                                  \
   if (pair && bn == BN) {                                                                     \
     const int rc = (p.resident && p.group) ? launch<BN, 64, 3, true>(ctx, amap, L, p, smem_bytes, st) \
