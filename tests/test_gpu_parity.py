@@ -672,3 +672,37 @@ def test_cta_pairs_give_bit_identical_results(cuda_device, monkeypatch):
         labels = rec.predict_device(x).clone()
         logits.append((labels, rec.tap("logits", (9, 48, 37), torch.float32).clone()))
     assert torch.equal(logits[0][0], logits[1][0]) and torch.equal(logits[0][1], logits[1][1])
+
+
+@pytest.mark.skipif(os.environ.get("B2O_EXPERIMENTAL") != "1",
+                    reason="opt-in kernel variants that have not run on a GPU yet: B2O_EXPERIMENTAL=1 pytest -m gpu -k experimental")
+@pytest.mark.parametrize("switch", [("B2O_TC_BOX16", "1"), ("B2O_TC_PAIR", "2")], ids=["box16", "generic_pairs"])
+def test_experimental_conv_variants_are_bit_identical(cuda_device, monkeypatch, switch):
+    """The opt-in convolution variants (one 16 x 18 A box per K chunk; CTA pairs on generic tiles) keep the MMA order of
+    the default path, so CRAFT score maps and CRNN logits must not change by a bit."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.recognition import Recognizer
+    cw, rw = W.synthetic_craft_weights(3), W.synthetic_crnn_weights(2)
+
+    def build(on):
+        if on:
+            monkeypatch.setenv(*switch)
+        else:
+            monkeypatch.delenv(switch[0], raising=False)
+        det, rec = Detector(weights=cw), Recognizer(weights=rw)
+        rec.keep_workspace = True
+        return det, rec
+
+    (det1, rec1), (det0, rec0) = build(True), build(False)
+    rng = np.random.default_rng(2)
+    for h, w in ((160, 224), (144, 200), (768, 768)):
+        img = torch.from_numpy(rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)).to(cuda_device)
+        assert torch.equal(det1.predict_device(img), det0.predict_device(img)), (h, w)
+    crops = torch.from_numpy(rng.integers(0, 256, (9, 31, 200), dtype=np.uint8)).to(cuda_device)
+    got = []
+    for rec in (rec1, rec0):
+        x = torch.empty((9, 200, 31), dtype=torch.float16, device=cuda_device)
+        rec.ctx.crops_to_input(crops.data_ptr(), 9, x.data_ptr(), _stream())
+        labels = rec.predict_device(x).clone()
+        got.append((labels, rec.tap("logits", (9, 48, 37), torch.float32).clone()))
+    assert torch.equal(got[0][0], got[1][0]) and torch.equal(got[0][1], got[1][1])
