@@ -15,8 +15,10 @@
 //   filter bank fits in shared memory (small layers) it is loaded once per CTA and stays resident.
 // * K chunk KCH = 64 / 32 / 16 channels (128B / 64B / 32B swizzle) so 32- and 16-channel layers
 //   (CRAFT conv_cls.*, STN) also run on the tensor cores.
-// * one elected thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N, K=16); fp32
-//   accumulators live in TMEM (2 stages): the epilogue of tile i overlaps the main loop of tile i+1.
+// * one elected thread issues tcgen05.mma.kind::f16 (N=BLOCK_N, K=16); fp32 accumulators live in TMEM (2-8
+//   stages): the epilogue of tile i overlaps the main loop of tile i+1.  3x3 layers with 64-channel chunks and
+//   N >= 64 run as CTA PAIRS (clusters of two CTAs on one TPC, cta_group::2, M=256: each CTA stages its own A
+//   tile and half of the B tile, the leader issues for both); the rest use cta_group::1 with M=128.
 // * warp roles: warp0 = TMA producer (A ring + B ring), warp1 = TMEM allocator + MMA issuer,
 //   warps 3..18 = epilogue: tcgen05.ld -> scale/shift/ReLU/affine -> fp16|fp32 NHWC stores (possibly
 //   into a channel slice of a concat buffer) and, optionally, the fused 2x2 max-pool output.
