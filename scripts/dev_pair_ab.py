@@ -1,8 +1,9 @@
-"""Development A/B: CTA pairs (tcgen05 cta_group::2, the default) against single-CTA tiles (B2O_TC_PAIR=0 at context
-creation), alternated in ONE process on ONE box.  Prints whether the score maps / labels are bit-identical
-(the accumulation order per output is the same) and the step / conv-kernel times of both.
+"""Development A/B of a context-creation switch, both settings alternated in ONE process on ONE box: prints whether the
+score maps / recognised texts are bit-identical and the step / conv-kernel times of both.
 
-    python scripts/dev_pair_ab.py            # PAGES=32 by default
+    python scripts/dev_pair_ab.py                        # B2O_TC_PAIR 0 (single-CTA tiles) vs 1 (CTA pairs, the default)
+    python scripts/dev_pair_ab.py B2O_TC_BOX16 0 1       # any other switch: VARIABLE off-value on-value
+    python scripts/dev_pair_ab.py B2O_TC_PAIR 1 2        # generic-tile pairs on top of the default
 """
 import os
 import sys
@@ -17,11 +18,14 @@ from keras_ocr_b200.recognition import Recognizer
 from oracle import synth
 
 
-def make(pair):
-    os.environ["B2O_TC_PAIR"] = "1" if pair else "0"
+VAR, OFF, ON = (sys.argv[1:4] + ["B2O_TC_PAIR", "0", "1"][len(sys.argv) - 1:])[:3] if len(sys.argv) > 1 else ("B2O_TC_PAIR", "0", "1")
+
+
+def make(on):
+    os.environ[VAR] = ON if on else OFF
     det = Detector(weights=W.synthetic_craft_weights(3, textlike=True))
     rec = Recognizer(weights=W.synthetic_crnn_weights(2))
-    os.environ.pop("B2O_TC_PAIR", None)
+    os.environ.pop(VAR, None)
     return Pipeline(detector=det, recognizer=rec, scale=2)
 
 
@@ -55,7 +59,7 @@ def main():
         p.detector.ctx.profile_enable(0); p.recognizer.ctx.profile_enable(0)
         res[k].append((e0.elapsed_time(e1), ms_d, ms_r))
     for k in (0, 1):
-        print("pair" if k else "single", " | ".join(f"step {a:.2f} conv craft {b:.2f} crnn {c:.2f}" for a, b, c in res[k]))
+        print(f"{VAR}={ON if k else OFF}", " | ".join(f"step {a:.2f} conv craft {b:.2f} crnn {c:.2f}" for a, b, c in res[k]))
 
 
 if __name__ == "__main__":
