@@ -209,12 +209,24 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # opt-in (B2O_BENCH_STREAM=1, N > 1; not yet run on GPUs): the K steps as a stream, rank 0 decoding step k-1's
+    # gathered words while every GPU already works on step k (distributed.ShardedStream); all K results are
+    # produced inside the timed region (the last one by flush()).
+    stream = D.ShardedStream(pipe, max_boxes=max_boxes) if world > 1 and os.environ.get("B2O_BENCH_STREAM") == "1" else None
+
     def timed(inputs, steps):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(steps):
-            step(inputs)
+        if stream is not None:
+            for _ in range(steps):
+                stream.submit(inputs)
+            result = stream.flush()
+            if result is not None:
+                stats["words"] = sum(len(g) for g in result)
+        else:
+            for _ in range(steps):
+                step(inputs)
         e1.record()
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
@@ -267,7 +279,8 @@ def run_b200(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "fp16", "data": "synthetic", "config": workload_config(world),
+        "dtype": "fp16", "data": "synthetic",
+        "config": dict(workload_config(world), **({"host_decode": "pipelined one step deep (ShardedStream)"} if stream else {})),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),

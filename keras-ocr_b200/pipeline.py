@@ -191,23 +191,38 @@ class Pipeline:
         pixels | rec_boxes x 48 int8 labels] (``distributed.unpack_blocks`` decodes it; rows beyond ``len(images)``
         carry count -1).  This is the payload of the multi-GPU gather: only the per-image box
         counts ever reach the host on this rank."""
+        return self.records_end(self.records_begin(images, rows, rec_boxes, detection_kwargs))
+
+    def records_begin(self, images, rows=None, rec_boxes=128, detection_kwargs=None):
+        """First half of ``recognize_records``: queues resize/pad, CRAFT and getBoxes and returns at once (no
+        synchronisation), so the caller can use the host while the GPU works (``distributed.ShardedStream`` decodes the
+        previous batch's words here).  Pass the returned state to ``records_end``."""
         assert self._native(), "recognize_records needs this package's Detector and Recognizer"
         if not isinstance(images, (np.ndarray, torch.Tensor)):
             images = [tools.read(image) for image in images]
-        det, rec = self.detector, self.recognizer
         thresholds = {k: v for k, v in (detection_kwargs or {}).items()
                       if k in ("detection_threshold", "text_threshold", "link_threshold", "size_threshold")}
         n = len(images)
         rows = n if rows is None else int(rows)
         assert rows >= n and rows > 0
         self.last_stats = {"h2d_bytes": 0, "d2h_bytes": 0}
+        state = {"n": n, "rows": rows, "rec_boxes": rec_boxes}
+        if n:
+            plans = self._plans(images)
+            state["st"] = self._stage_detect(images, (max(p[1] for p in plans), max(p[2] for p in plans)), thresholds)
+        return state
+
+    def records_end(self, state):
+        """Second half of ``recognize_records``: waits for the box counts (the path's one synchronisation), queues
+        warp + CRNN + ``b2o_pack_records`` and returns the CUDA record tensor."""
+        det, rec = self.detector, self.recognizer
+        n, rows, rec_boxes = state["n"], state["rows"], state["rec_boxes"]
         records = torch.empty((rows, det.ctx.record_floats(rec_boxes)), dtype=torch.float32, device=det.device)
         if n == 0:
             records.zero_()
             records[:, 0] = -1
             return records
-        plans = self._plans(images)
-        st = self._stage_detect(images, (max(p[1] for p in plans), max(p[2] for p in plans)), thresholds)
+        st = state["st"]
         bst = st.pop("boxes_state")
         boxes, counts = det.boxes_finish(bst)
         labels = rec.recognize_from_boxes_device(st["batch"], boxes, counts, gray=st["gray"], flat=bst["flat"],

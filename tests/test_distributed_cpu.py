@@ -59,6 +59,56 @@ class _FakeRecordsPipeline(_FakePipeline):
         return D._host_records(_FakePipeline(), images, rows, rec_boxes)
 
 
+class _FakeTwoPhasePipeline(_FakePipeline):
+    """Offers records_begin / records_end like the real Pipeline (the stream decodes between the two)."""
+
+    def records_begin(self, images, rows=None, rec_boxes=128):
+        return {"images": images, "rows": rows, "rec_boxes": rec_boxes}
+
+    def records_end(self, state):
+        return D._host_records(_FakePipeline(), state["images"], state["rows"], state["rec_boxes"])
+
+
+def _stream_worker(rank, world, port, batches, ret, two_phase):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        stream = D.ShardedStream(_FakeTwoPhasePipeline() if two_phase else _FakePipeline(), max_boxes=8)
+        outs = [stream.submit(b[rank * 2:(rank + 1) * 2]) for b in batches]      # two images per rank and batch
+        outs.append(stream.flush())
+        assert stream.flush() is None                                             # nothing left in flight
+        if rank == 0:
+            ret.put([None if o is None else [[(t, b.tolist()) for t, b in g] for g in o] for o in outs])
+        else:
+            assert all(o is None for o in outs)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("two_phase", [False, True])
+def test_sharded_stream_is_one_batch_deep_and_ordered(two_phase):
+    """ShardedStream.submit(batch k) returns batch k-1's results on rank 0 (None first), flush() the last; global image
+    order and payload are those of recognize_sharded."""
+    batches = []
+    for k in range(3):
+        im = np.zeros((4, 4, 4, 3), np.uint8)
+        im[:, 0, 0, 0] = np.arange(4) + 1 + 4 * k
+        batches.append(im)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_stream_worker, args=(r, 2, port, batches, ret, two_phase)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    expect = [[[(t, b.tolist()) for t, b in g] for g in _FakePipeline().recognize(b)] for b in batches]
+    assert got[0] is None and got[1:] == expect
+
+
 def _worker(rank, world, port, images, ret, kind="host", presharded=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
