@@ -142,9 +142,12 @@ int b2o_pack_records(b2o_ctx* ctx, const float* boxes_dev, const int32_t* counts
                      const float* inv_scale_dev, int n, int max_boxes, int rows, int rec_boxes,
                      float* records_dev, void* stream);
 
-/* Debug / test taps (not on the product path): copy an intermediate of the last forward pass.
+/* Debug / test taps (not on the product path): b2o_set_debug_taps(ctx, 1) makes b2o_crnn_forward also write the
+ * fp32 fc_12 outputs ("logits") to its workspace; by default (0) the fused Dense + CTC kernel keeps them in
+ * registers and only the labels reach memory.  b2o_crnn_tap copies an intermediate of the last forward pass.
  * b2o_crnn_tap names: "features" (b,50,7,512 f16), "theta" (b,6 f32), "warped" (b,50,7,512 f16),
  * "fc_9" (b,50,128 f16), "l1" (b,50,128 f16), "l2" (b,50,256 f16), "logits" (b,48,K f32).      */
+int b2o_set_debug_taps(b2o_ctx* ctx, int on);
 int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws_dev, int b, void* out_dev,
                  size_t out_bytes, void* stream);
 

@@ -54,6 +54,7 @@ SIGNATURES = {
     "b2o_crnn_workspace_bytes": (_sz, [_i]),
     "b2o_crops_to_input": (_i, [_vp, _vp, _i, _vp, _vp]),
     "b2o_crnn_forward": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
+    "b2o_set_debug_taps": (_i, [_vp, _i]),
     "b2o_crnn_tap": (_i, [_vp, _c.c_char_p, _vp, _i, _vp, _sz, _vp]),
     "b2o_conv2d_test": (_i, [_vp, _vp, _i, _i, _i, _i, _c.POINTER(_c.c_float), _i, _i, _i,
                              _c.POINTER(_c.c_float), _c.POINTER(_c.c_float), _i,
@@ -196,6 +197,9 @@ class Context:
 
     def crnn_forward(self, crnn_in, b, labels, ws, ws_bytes, stream):
         self._check(self.lib.b2o_crnn_forward(self.handle, crnn_in, b, labels, ws, ws_bytes, stream), "b2o_crnn_forward")
+
+    def set_debug_taps(self, on):
+        self._check(self.lib.b2o_set_debug_taps(self.handle, int(on)), "b2o_set_debug_taps")
 
     def crnn_tap(self, name, ws, b, out, out_bytes, stream):
         self._check(self.lib.b2o_crnn_tap(self.handle, name.encode(), ws, b, out, out_bytes, stream), "b2o_crnn_tap")

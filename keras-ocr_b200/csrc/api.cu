@@ -178,7 +178,7 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   *out = nullptr;
   int count = 0;
   if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) return B2O_ERR_CUDA;
-  if (cudaSetDevice(device) != cudaSuccess) return B2O_ERR_CUDA;
+  DeviceGuard guard(device);                  // the caller's current device is restored on return
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return B2O_ERR_CUDA;
   if (prop.major != 10) {
@@ -200,9 +200,11 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
 
 extern "C" void b2o_destroy(b2o_ctx* ctx) {
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
-  for (void* p : ctx->owned) cudaFree(p);
-  for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  {
+    DeviceGuard guard(ctx->device);
+    for (void* p : ctx->owned) cudaFree(p);
+    for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+  }
   delete ctx;
 }
 
@@ -220,6 +222,7 @@ extern "C" int b2o_profile_enable(b2o_ctx* ctx, int on) {
 
 extern "C" int b2o_profile_read(b2o_ctx* ctx, double* tc_ms, double* tc_flop, int64_t* tc_launches) {
   if (!ctx || !tc_ms || !tc_flop || !tc_launches) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   double ms = 0.0;
   for (size_t i = 0; i + 1 < ctx->prof_events.size(); i += 2) {
     B2O_CUDA_CHECK(ctx, cudaEventSynchronize(ctx->prof_events[i + 1]));
@@ -241,7 +244,7 @@ extern "C" int b2o_set_conv_engine(b2o_ctx* ctx, int engine) {
 
 extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
   if (!ctx || !tensors) return B2O_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
   TensorMap m;
   for (int i = 0; i < n; ++i) m[tensors[i].name] = &tensors[i];
   for (const CraftSpec& s : kCraft) {
@@ -274,6 +277,7 @@ extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
       };
       ConvLayer& L16 = ctx->craft["stem16"];
       B2O_RETURN_IF(build_layer(ctx, L16, "stem16", 16, s.cout, s.k, 1, s.relu, wget16, s1, t1, nullptr, nullptr, false));
+      L16.alg_cin = 3;
     }
   }
   ctx->craft_loaded = true;
@@ -282,7 +286,7 @@ extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
 
 extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
   if (!ctx || !tensors) return B2O_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
   TensorMap m;
   for (int i = 0; i < n; ++i) m[tensors[i].name] = &tensors[i];
   struct Spec { const char* name; int cin, cout, k; const char* bn; };
@@ -327,6 +331,7 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
       ConvLayer& G = ctx->crnn["stn.conv_a_gemm"];
       B2O_RETURN_IF(build_layer(ctx, G, "stn.conv_a_gemm", s.cin, 512, 1, 1, 0, wgemm, ones(512),
                                 std::vector<float>(512, 0.0f), nullptr, nullptr, false));
+      G.alg_cout = k * k * cout;                 // 400 of the 512 columns are real
     }
   }
   // dense layers as 1x1 "convolutions" over a (1,1,rows,K) view
@@ -407,6 +412,7 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
                                  size_t ws_bytes, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
   if (!ctx->craft_loaded) { ctx->set_error("b2o_craft_forward: CRAFT weights not loaded"); return B2O_ERR_STATE; }
+  DeviceGuard guard(ctx->device);
   if (!img || !scores || !ws || n <= 0 || h < 32 || w < 32) { ctx->set_error("b2o_craft_forward: bad argument"); return B2O_ERR_ARG; }
   const CraftPlan p = plan_craft(n, h, w);
   if (ws_bytes < p.bytes) { ctx->set_error("b2o_craft_forward: workspace too small"); return B2O_ERR_WORKSPACE; }
@@ -485,6 +491,7 @@ extern "C" int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in, int b, int32_
                                 void* stream) {
   if (!ctx) return B2O_ERR_ARG;
   if (!ctx->crnn_loaded) { ctx->set_error("b2o_crnn_forward: CRNN weights not loaded"); return B2O_ERR_STATE; }
+  DeviceGuard guard(ctx->device);
   if (b == 0) return B2O_OK;
   if (!crnn_in || !labels || !ws || b < 0) { ctx->set_error("b2o_crnn_forward: bad argument"); return B2O_ERR_ARG; }
   const CrnnPlan p = plan_crnn(b);
@@ -541,12 +548,19 @@ extern "C" int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in, int b, int32_
   B2O_RETURN_IF(lstm_run(ctx, xw2f, 1024, 0, ctx->lstm_u[2], b, 0, l2, 256, 0, st));
   B2O_RETURN_IF(lstm_run(ctx, xw2f, 1024, 512, ctx->lstm_u[3], b, 1, l2, 256, 128, st));
   // fc_12 + discard + greedy CTC (321-333)
-  B2O_RETURN_IF(fc_ctc_run(ctx, l2, b, reinterpret_cast<float*>(base + p.off_logits), labels, st));
+  B2O_RETURN_IF(fc_ctc_run(ctx, l2, b, ctx->debug_taps ? reinterpret_cast<float*>(base + p.off_logits) : nullptr, labels, st));
+  return B2O_OK;
+}
+
+extern "C" int b2o_set_debug_taps(b2o_ctx* ctx, int on) {
+  if (!ctx) return B2O_ERR_ARG;
+  ctx->debug_taps = on != 0;
   return B2O_OK;
 }
 
 extern "C" int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws, int b, void* out, size_t out_bytes, void* stream) {
   if (!ctx || !name || !ws || !out || b <= 0) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   const CrnnPlan p = plan_crnn(b);
   const size_t B = static_cast<size_t>(b);
   size_t off = 0, bytes = 0;
@@ -557,7 +571,10 @@ extern "C" int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws, int 
   else if (s == "fc_9") { off = p.off_fc9; bytes = B * 50 * 128 * 2; }
   else if (s == "l1") { off = p.off_l1; bytes = B * 50 * 128 * 2; }
   else if (s == "l2") { off = p.off_l2; bytes = B * 50 * 256 * 2; }
-  else if (s == "logits") { off = p.off_logits; bytes = B * 48 * ctx->n_classes * 4; }
+  else if (s == "logits") {
+    if (!ctx->debug_taps) { ctx->set_error("b2o_crnn_tap: logits are only kept after b2o_set_debug_taps(ctx, 1)"); return B2O_ERR_STATE; }
+    off = p.off_logits; bytes = B * 48 * ctx->n_classes * 4;
+  }
   else { ctx->set_error("b2o_crnn_tap: unknown tap " + s); return B2O_ERR_ARG; }
   if (out_bytes < bytes) { ctx->set_error("b2o_crnn_tap: output too small"); return B2O_ERR_ARG; }
   B2O_CUDA_CHECK(ctx, cudaMemcpyAsync(out, reinterpret_cast<const uint8_t*>(ws) + off, bytes, cudaMemcpyDeviceToDevice,
@@ -569,7 +586,7 @@ extern "C" int b2o_conv2d_test(b2o_ctx* ctx, const void* x, int n, int h, int w,
                                int ksize, int dilation, const float* s1, const float* t1, int relu, const float* s2,
                                const float* t2, void* out, int engine, void* stream) {
   if (!ctx || !x || !wgt || !s1 || !t1 || !out) return B2O_ERR_ARG;
-  cudaSetDevice(ctx->device);
+  DeviceGuard guard(ctx->device);
   const size_t owned_before = ctx->owned.size();
   ConvLayer L;
   auto wget = [wgt, cin, ksize](int o, int c, int ky, int kx) {

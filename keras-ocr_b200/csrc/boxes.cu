@@ -636,6 +636,7 @@ extern "C" int b2o_get_boxes(b2o_ctx* ctx, const float* scores, int n, int hs, i
                              float text_threshold, float link_threshold, int size_threshold, float* boxes,
                              int32_t* counts, int max_boxes, void* ws_dev, size_t ws_bytes, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (!scores || !boxes || !counts || !ws_dev || n <= 0 || hs <= 0 || ws <= 0 || max_boxes <= 0) {
     ctx->set_error("b2o_get_boxes: bad argument");
     return B2O_ERR_ARG;
@@ -725,14 +726,17 @@ pack_records_kernel(const float* __restrict__ boxes, const int32_t* __restrict__
   const int rec_len = 1 + rec_boxes * 8 + rec_boxes * (kSteps / 4);
   float* r = rec + static_cast<size_t>(row) * rec_len;
   int8_t* lab = reinterpret_cast<int8_t*>(r + 1 + rec_boxes * 8);
-  int c = 0, off = 0;
+  int c = 0, off = 0, held = 0;
   float inv = 1.f;
   if (row < n) {                                   // uniform per block
     off = boxes_before(counts, row, max_boxes);
-    c = min(min(max(counts[row], 0), max_boxes), rec_boxes);
+    held = min(max(counts[row], 0), max_boxes);      // boxes of this image in the table
+    c = min(held, rec_boxes);                        // ... of which the record has room for c
     inv = inv_scale[row];
   }
-  if (threadIdx.x == 0) r[0] = row < n ? static_cast<float>(c) : -1.f;    // -1: padding row of a short shard
+  // count field: what the image HAS (the reader refuses a record whose count exceeds rec_boxes instead of silently
+  // dropping words); -1 marks the padding rows of a short shard
+  if (threadIdx.x == 0) r[0] = row < n ? static_cast<float>(held) : -1.f;
   const float* src = boxes + static_cast<size_t>(min(row, n - 1)) * max_boxes * 8;
   for (int t = threadIdx.x; t < rec_boxes * 8; t += blockDim.x)
     r[1 + t] = t < c * 8 ? __fmul_rn(src[t], inv) : 0.f;                  // tools.adjust_boxes (tools.py:232-260)
@@ -748,6 +752,7 @@ pack_records_kernel(const float* __restrict__ boxes, const int32_t* __restrict__
 extern "C" int b2o_compact_boxes(b2o_ctx* ctx, const float* boxes, const int32_t* counts, int n, int max_boxes,
                                  float* flat, int32_t* image_index, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (!boxes || !counts || !flat || !image_index || n <= 0 || max_boxes <= 0) {
     ctx->set_error("b2o_compact_boxes: bad argument");
     return B2O_ERR_ARG;
@@ -766,6 +771,7 @@ extern "C" int b2o_pack_records(b2o_ctx* ctx, const float* boxes, const int32_t*
                                 const float* inv_scale, int n, int max_boxes, int rows, int rec_boxes, float* records,
                                 void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (!boxes || !counts || !inv_scale || !records || n <= 0 || rows < n || max_boxes <= 0 || rec_boxes <= 0) {
     ctx->set_error("b2o_pack_records: bad argument");      // labels may be NULL when no image has a box
     return B2O_ERR_ARG;

@@ -33,6 +33,21 @@
     }                                                                                          \
   } while (0)
 
+// Every entry point that touches the device runs with the context's device current and puts the caller's device
+// back on return (the caller -- torch -- may be driving another GPU of the box in the same process).
+struct DeviceGuard {
+  int prev = -1;
+  bool changed = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) changed = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (changed) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
 #define B2O_RETURN_IF(expr)                                                                    \
   do {                                                                                         \
     int _s = (expr);                                                                           \
@@ -56,6 +71,9 @@ struct ConvLayer {
   bool pair_ok = false;        // wmap_pair is valid (64-channel chunks, block_n >= 64)
   int block_n = 0;             // tcgen05 N tile; 0 = layer not eligible for the tensor-core engine
   int kch = 0;                 // tcgen05 K chunk (channels per stage): 64 / 32 / 16
+  // channels of the layer the reference defines, where the tensor-core form pads them (3 -> 16 input channels of the
+  // CRAFT stem, 400 -> 512 columns of the STN GEMM): what the roofline's algorithmic FLOP count uses.  0 = cin / cout.
+  int alg_cin = 0, alg_cout = 0;
 };
 
 struct TensorView {            // NHWC fp16 activation living inside a (possibly wider) buffer
@@ -85,6 +103,7 @@ struct b2o_ctx {
   int n_classes = 37;                                          // K (last index = CTC blank), <= B2O_MAX_CLASSES
   std::vector<void*> owned;    // device allocations freed in b2o_destroy
   // optional per-launch timing of the tensor-core conv kernel (bench.py's roofline leg)
+  bool debug_taps = false;     // b2o_set_debug_taps: the CRNN forward also writes its fp32 logits (tests only)
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // (start, stop) pairs
   double prof_flop = 0.0;

@@ -875,8 +875,10 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     B2O_CUDA_CHECK(ctx, cudaEventRecord(e1, st));
     ctx->prof_events.push_back(e0);
     ctx->prof_events.push_back(e1);
-    // algorithmic FLOPs of this launch: 2 * pixels * (taps * cin) * cout
-    ctx->prof_flop += 2.0 * double(p.N) * p.H * p.W * double(p.ksize * p.ksize) * p.cin * p.cout;
+    // algorithmic FLOPs of this launch: 2 * pixels * (taps * cin) * cout with the REFERENCE layer's channel counts
+    // (SURVEY.md 8(d)): the zero-padded channels of the stem (3 -> 16) and of the STN GEMM (400 -> 512) do not count
+    ctx->prof_flop += 2.0 * double(p.N) * p.H * p.W * double(p.ksize * p.ksize) * (L.alg_cin ? L.alg_cin : p.cin) *
+                      (L.alg_cout ? L.alg_cout : p.cout);
   }
   return B2O_OK;
 }

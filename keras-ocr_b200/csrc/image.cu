@@ -245,6 +245,7 @@ __global__ void crops_to_input_kernel(const uint8_t* __restrict__ crops, long lo
 extern "C" int b2o_resize_pad(b2o_ctx* ctx, const uint8_t* src, int hs, int ws, int hr, int wr, uint8_t* dst,
                               int index, int hp, int wp, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (!src || !dst || hs <= 0 || ws <= 0 || hr <= 0 || wr <= 0 || hr > hp || wr > wp || index < 0) {
     ctx->set_error("b2o_resize_pad: bad argument (resized image must fit the padded size)");
     return B2O_ERR_ARG;
@@ -261,6 +262,7 @@ extern "C" int b2o_resize_pad(b2o_ctx* ctx, const uint8_t* src, int hs, int ws, 
 extern "C" int b2o_resize_pad_batch(b2o_ctx* ctx, const uint8_t* src, int n, int hs, int ws, int hr, int wr,
                                     uint8_t* dst, int hp, int wp, uint8_t* gray, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (!src || !dst || n <= 0 || n > 65535 || hs <= 0 || ws <= 0 || hr <= 0 || wr <= 0 || hr > hp || wr > wp || hp > 65535) {
     ctx->set_error("b2o_resize_pad_batch: bad argument (resized image must fit the padded size)");
     return B2O_ERR_ARG;
@@ -273,6 +275,7 @@ extern "C" int b2o_resize_pad_batch(b2o_ctx* ctx, const uint8_t* src, int n, int
 
 extern "C" int b2o_rgb_to_gray(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, uint8_t* gray, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (!img || !gray || n <= 0 || h <= 0 || w <= 0) { ctx->set_error("b2o_rgb_to_gray: bad argument"); return B2O_ERR_ARG; }
   const long long total = static_cast<long long>(n) * h * w;
   gray_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(img, total, gray);
@@ -283,6 +286,7 @@ extern "C" int b2o_rgb_to_gray(b2o_ctx* ctx, const uint8_t* img, int n, int h, i
 extern "C" int b2o_warp_boxes(b2o_ctx* ctx, const uint8_t* gray, int n, int h, int w, const float* boxes,
                               const int32_t* image_index, int n_boxes, uint8_t* crops, void* crnn_in, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (n_boxes == 0) return B2O_OK;
   if (!gray || !boxes || !image_index || n <= 0 || h <= 0 || w <= 0 || n_boxes < 0 || (!crops && !crnn_in)) {
     ctx->set_error("b2o_warp_boxes: bad argument");
@@ -296,6 +300,7 @@ extern "C" int b2o_warp_boxes(b2o_ctx* ctx, const uint8_t* gray, int n, int h, i
 
 extern "C" int b2o_crops_to_input(b2o_ctx* ctx, const uint8_t* crops, int b, void* crnn_in, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
   if (b == 0) return B2O_OK;
   if (!crops || !crnn_in || b < 0) { ctx->set_error("b2o_crops_to_input: bad argument"); return B2O_ERR_ARG; }
   const long long total = static_cast<long long>(b) * kCropH * kCropW;

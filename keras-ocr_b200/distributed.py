@@ -32,7 +32,7 @@ def pack_records(counts, boxes, labels, per_rank, max_boxes):
     start = 0
     for i in range(n):
         c = min(int(counts[i]), max_boxes)
-        rec[i, 0] = c
+        rec[i, 0] = int(counts[i])                     # what the image HAS; unpack_blocks refuses counts > max_boxes
         rec[i, 1:1 + c * 8] = np.asarray(boxes[i][:c], dtype=np.float32).reshape(-1)
         if c:
             lab8[i, :c] = np.asarray(labels[start:start + c], dtype=np.int8)
@@ -49,18 +49,32 @@ def unpack_records(rec, max_boxes):
     return [(int(c), boxes[e - c:e], labels[e - c:e].astype(np.int32)) for c, e in zip(counts, ends)]
 
 
-def unpack_blocks(blocks, max_boxes):
+class RecordOverflow(ValueError):
+    """An image has more words than a fixed-size record holds (``max_boxes``)."""
+
+
+def unpack_blocks(blocks, max_boxes, strict=True):
     """All gathered blocks at once (rank order = global image order): returns (counts (n_images,), boxes (total,4,2)
     float32, labels (total,48) int8) with the words of image i at [sum(counts[:i]), +counts[i]).  Only the used
-    prefix of every record is touched (two concatenations of per-image views), not the 75 % padding."""
+    prefix of every record is touched (two concatenations of per-image views), not the 75 % padding.
+
+    A record's count field is the number of words its image HAS; a record holds ``max_boxes`` of them.  The
+    single-GPU ``Pipeline.recognize`` grows its box table on demand (as the reference returns every box), so a
+    count above ``max_boxes`` raises ``RecordOverflow`` rather than dropping words (``strict=False``: keep the
+    first ``max_boxes``, for callers that asked for a cap)."""
     box_parts, lab_parts, counts = [], [], []
     lab0 = (1 + max_boxes * 8) * 4                     # byte offset of the label area inside a record
-    for block in blocks:
+    for r, block in enumerate(blocks):
         rec = np.ascontiguousarray(np.asarray(block.cpu() if isinstance(block, torch.Tensor) else block))
         rec8 = rec.view(np.int8)
         for i, c in enumerate(rec[:, 0].astype(np.int64).tolist()):
             if c < 0:                                  # padding row of a short shard
                 continue
+            if c > max_boxes:
+                if strict:
+                    raise RecordOverflow(f"image {i} of rank {r} has {c} words but the gathered records hold "
+                                         f"max_boxes={max_boxes}: pass a larger max_boxes (or max_boxes='auto')")
+                c = max_boxes
             counts.append(c)
             if c:
                 box_parts.append(rec[i, 1:1 + c * 8])
@@ -81,9 +95,8 @@ def gather_records(local, world_size, rank, device=None):
     return blocks
 
 
-def _host_records(pipeline, images, per_rank, max_boxes):
-    """Record block of a duck-typed pipeline: run its ``recognize`` and pack the (word, box) lists on the host."""
-    local = pipeline.recognize(images) if len(images) else []
+def _host_records(pipeline, local, per_rank, max_boxes):
+    """Record block of a duck-typed pipeline: pack the (word, box) lists its ``recognize`` returned on the host."""
     alphabet = pipeline.recognizer.alphabet
     counts = [len(g) for g in local]
     boxes = [np.array([b for _, b in g], dtype=np.float32).reshape(-1, 4, 2) for g in local]
@@ -120,16 +133,48 @@ def recognize_sharded(pipeline, images, max_boxes=128, presharded=False):
     assert len(alphabet) + 1 <= 127, "record labels travel as int8: alphabets up to 126 characters"
     if per_rank == 0:
         return [] if rank == 0 else None
-    if getattr(pipeline, "recognize_records", None) is not None and getattr(pipeline, "_native", lambda: True)():
-        local = pipeline.recognize_records(mine, rows=per_rank, rec_boxes=max_boxes)
+    native = getattr(pipeline, "recognize_records", None) is not None and getattr(pipeline, "_native", lambda: True)()
+    if native:
+        if getattr(pipeline, "records_counts", None) is not None:
+            state = pipeline.records_begin(mine, rows=per_rank, rec_boxes=16 if max_boxes == "auto" else max_boxes)
+            if max_boxes == "auto":
+                max_boxes = agree_max_boxes(pipeline.records_counts(state), _collective_device(pipeline))
+            local = pipeline.records_end(state, rec_boxes=max_boxes)
+        else:                                           # a pipeline that only offers the one-call form
+            assert max_boxes != "auto", "max_boxes='auto' needs records_begin / records_counts / records_end"
+            local = pipeline.recognize_records(mine, rows=per_rank, rec_boxes=max_boxes)
         device = None                                   # already where the backend wants it
     else:
-        local = _host_records(pipeline, mine, per_rank, max_boxes)
-        device = pipeline.detector.device if dist.is_initialized() and dist.get_backend() == "nccl" else None
+        result = pipeline.recognize(mine) if len(mine) else []
+        if max_boxes == "auto":
+            max_boxes = agree_max_boxes([len(g) for g in result], _collective_device(pipeline))
+        local = _host_records(pipeline, result, per_rank, max_boxes)
+        device = _collective_device(pipeline)
     blocks = gather_records(local, world, rank, device)
     if rank != 0:
         return None
     return _decode_blocks(blocks, max_boxes, alphabet)
+
+
+def _collective_device(pipeline):
+    """Where tensors must live for the process group's collectives: the GPU under NCCL, the host under gloo."""
+    return pipeline.detector.device if dist.is_initialized() and dist.get_backend() == "nccl" else None
+
+
+def agree_max_boxes(counts, device=None, floor=16):
+    """``max_boxes='auto'``: every rank contributes its largest per-image word count; ONE all-reduce (MAX) of a
+    single int gives the record size all ranks use for this batch (next power of two, at least ``floor``), so a dense
+    page costs nothing on sparse batches and nothing is ever dropped.  Costs one extra tiny collective + sync per
+    batch, which is why a fixed ``max_boxes`` (overflow = ``RecordOverflow`` on rank 0) stays the default."""
+    local = int(max(counts)) if len(counts) else 0
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.tensor([local], dtype=torch.int32, device=device if device is not None else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        local = int(t.item())
+    size = floor
+    while size < local:
+        size *= 2
+    return size
 
 
 def _decode_blocks(blocks, max_boxes, alphabet):
@@ -155,7 +200,9 @@ class ShardedStream:
         last = stream.flush()                # rank 0: results of the last batch
 
     With this package's ``Pipeline`` the records stay on the device until the gather and reach the host through ONE
-    asynchronous copy into pinned memory; any other pipeline (``recognize`` only) is served too, without the overlap."""
+    asynchronous copy into pinned memory; any other pipeline (``recognize`` only) is served too, without the overlap.
+    ``max_boxes``: words a record holds (an image with more raises ``RecordOverflow`` on rank 0 when its batch is
+    decoded) or ``"auto"`` (sized per batch by ``agree_max_boxes``)."""
 
     def __init__(self, pipeline, max_boxes=128):
         self.pipeline, self.max_boxes = pipeline, max_boxes
@@ -171,26 +218,31 @@ class ShardedStream:
         if self._pending is None or self.rank != 0:
             self._pending = None
             return None
-        host, event = self._pending
+        host, event, max_boxes = self._pending
         self._pending = None
         if event is not None:
             event.synchronize()
-        return _decode_blocks(list(host), self.max_boxes, self.alphabet)
+        return _decode_blocks(list(host), max_boxes, self.alphabet)
 
     def submit(self, images):
         rows = len(images)
         if rows == 0:
             return self._take_pending()
+        max_boxes = self.max_boxes
         if self._native:
-            state = self.pipeline.records_begin(images, rows=rows, rec_boxes=self.max_boxes)   # GPU busy from here on
+            state = self.pipeline.records_begin(images, rows=rows, rec_boxes=16 if max_boxes == "auto" else max_boxes)   # GPU busy from here on
             previous = self._take_pending()              # ... while the host decodes the batch before
-            local = self.pipeline.records_end(state)
+            if max_boxes == "auto":
+                max_boxes = agree_max_boxes(self.pipeline.records_counts(state), _collective_device(self.pipeline))
+            local = self.pipeline.records_end(state, rec_boxes=max_boxes)
             device = None
         else:
             previous = self._take_pending()
-            local = _host_records(self.pipeline, images, rows, self.max_boxes)
-            device = (self.pipeline.detector.device
-                      if dist.is_initialized() and dist.get_backend() == "nccl" else None)
+            result = self.pipeline.recognize(images)
+            if max_boxes == "auto":
+                max_boxes = agree_max_boxes([len(g) for g in result], _collective_device(self.pipeline))
+            local = _host_records(self.pipeline, result, rows, max_boxes)
+            device = _collective_device(self.pipeline)
         blocks = gather_records(local, self.world, self.rank, device)
         if self.rank == 0:
             stacked = torch.stack(list(blocks))
@@ -199,10 +251,10 @@ class ShardedStream:
                 host.copy_(stacked, non_blocking=True)
                 event = torch.cuda.Event()
                 event.record(torch.cuda.current_stream(stacked.device))
-                self._pending = (host, event)
+                self._pending = (host, event, max_boxes)
                 self._keep = stacked                     # alive until the copy has run
             else:
-                self._pending = (stacked, None)
+                self._pending = (stacked, None, max_boxes)
         return previous
 
     def flush(self):

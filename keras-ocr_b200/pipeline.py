@@ -198,6 +198,7 @@ class Pipeline:
         synchronisation), so the caller can use the host while the GPU works (``distributed.ShardedStream`` decodes the
         previous batch's words here).  Pass the returned state to ``records_end``."""
         assert self._native(), "recognize_records needs this package's Detector and Recognizer"
+        assert len(self.recognizer.alphabet) + 1 <= 127, "record labels travel as int8: alphabets up to 126 characters"
         if not isinstance(images, (np.ndarray, torch.Tensor)):
             images = [tools.read(image) for image in images]
         thresholds = {k: v for k, v in (detection_kwargs or {}).items()
@@ -212,19 +213,34 @@ class Pipeline:
             state["st"] = self._stage_detect(images, (max(p[1] for p in plans), max(p[2] for p in plans)), thresholds)
         return state
 
-    def records_end(self, state):
+    def records_counts(self, state):
+        """Waits for the box counts of ``records_begin`` (the path's one synchronisation) and returns them (host
+        ndarray, one per image) -- what a caller needs to size ``rec_boxes`` before ``records_end``."""
+        if state["n"] == 0:
+            return np.zeros((0,), np.int32)
+        if "counts" not in state:
+            st = state["st"]
+            bst = st["boxes_state"]
+            state["boxes"], state["counts"] = self.detector.boxes_finish(bst)
+        return state["counts"]
+
+    def records_end(self, state, rec_boxes=None):
         """Second half of ``recognize_records``: waits for the box counts (the path's one synchronisation), queues
-        warp + CRNN + ``b2o_pack_records`` and returns the CUDA record tensor."""
+        warp + CRNN + ``b2o_pack_records`` and returns the CUDA record tensor.  A record holds ``rec_boxes`` words;
+        its count field carries what the image has, so the reader (``distributed.unpack_blocks``) notices an image
+        that does not fit instead of losing words."""
         det, rec = self.detector, self.recognizer
-        n, rows, rec_boxes = state["n"], state["rows"], state["rec_boxes"]
+        n, rows = state["n"], state["rows"]
+        rec_boxes = state["rec_boxes"] if rec_boxes is None else int(rec_boxes)
         records = torch.empty((rows, det.ctx.record_floats(rec_boxes)), dtype=torch.float32, device=det.device)
         if n == 0:
             records.zero_()
             records[:, 0] = -1
             return records
+        counts = self.records_counts(state)
         st = state["st"]
         bst = st.pop("boxes_state")
-        boxes, counts = det.boxes_finish(bst)
+        boxes = state["boxes"]
         labels = rec.recognize_from_boxes_device(st["batch"], boxes, counts, gray=st["gray"], flat=bst["flat"],
                                                  image_index=bst["image_index"])
         inv = torch.tensor([1.0 / s for s in st["scales"]], dtype=torch.float32).to(det.device, non_blocking=True)

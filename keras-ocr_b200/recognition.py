@@ -84,9 +84,20 @@ class Recognizer:
             tensors["fc_12.bias"] = np.zeros(n_classes, np.float32)
         self.ctx = _lib.Context(self.device_index)
         self.ctx.load_crnn(tensors)
-        self.keep_workspace = False      # tests set this to read intermediate taps
+        self._keep_workspace = False     # tests set keep_workspace to read intermediate taps
         self._last_ws = None
         self._ws = None                  # reusable CRNN workspace (grown on demand)
+
+    @property
+    def keep_workspace(self):
+        return self._keep_workspace
+
+    @keep_workspace.setter
+    def keep_workspace(self, on):
+        """Debug: keep the last forward pass's workspace for ``tap`` and make the CRNN write its fp32 logits
+        (off on the product path: the fused Dense + CTC kernel then stores labels only)."""
+        self._keep_workspace = bool(on)
+        self.ctx.set_debug_taps(self._keep_workspace)
 
     # ------------------------------------------------------------------ device-resident API
     def gray_device(self, images_t):

@@ -81,13 +81,15 @@ def random_word(rng, lo=3, hi=10):
     return "".join(ALPHABET[i] for i in rng.integers(0, len(ALPHABET), int(rng.integers(lo, hi + 1))))
 
 
-def text_image(rng, h, w, n_words):
-    """White RGB page with ``n_words`` random words on a jittered grid.  Returns (image, words)."""
+def text_image(rng, h, w, n_words, return_layout=False):
+    """White RGB page with ``n_words`` random words on a jittered grid.  Returns (image, words), or with
+    ``return_layout`` (image, words, rects) where rects[k] = (x0, y0, x1, y1) bounds word k's glyphs in page pixels
+    (same random stream either way, so the pages are identical)."""
     img = np.full((h, w, 3), 255, np.uint8)
     cols = max(1, int(np.floor(np.sqrt(n_words * w / h / 2.0))))
     rows = int(np.ceil(n_words / cols))
     cell_w, cell_h = w / cols, h / rows
-    words = []
+    words, rects = [], []
     for k in range(n_words):
         gx, gy = k % cols, k // cols
         word = random_word(rng)
@@ -95,12 +97,15 @@ def text_image(rng, h, w, n_words):
         (tw, th), _ = cv2.getTextSize(word, cv2.FONT_HERSHEY_SIMPLEX, scale, 2)
         fit = min(0.8 * cell_w / tw, 0.45 * cell_h / th)
         scale *= fit
-        (tw, th), _ = cv2.getTextSize(word, cv2.FONT_HERSHEY_SIMPLEX, scale, 2)
+        (tw, th), base = cv2.getTextSize(word, cv2.FONT_HERSHEY_SIMPLEX, scale, 2)
         x = int(gx * cell_w + (cell_w - tw) / 2 + rng.uniform(-0.05, 0.05) * cell_w)
         y = int(gy * cell_h + (cell_h + th) / 2 + rng.uniform(-0.05, 0.05) * cell_h)
         colour = tuple(int(c) for c in rng.integers(0, 90, 3))
         cv2.putText(img, word, (x, y), cv2.FONT_HERSHEY_SIMPLEX, scale, colour, 2, cv2.LINE_AA)
         words.append(word)
+        rects.append((x, y - th, x + tw, y + base))
+    if return_layout:
+        return img, words, rects
     return img, words
 
 

@@ -56,7 +56,7 @@ class _FakeRecordsPipeline(_FakePipeline):
 
     def recognize_records(self, images, rows=None, rec_boxes=128):
         type(self).calls += 1
-        return D._host_records(_FakePipeline(), images, rows, rec_boxes)
+        return D._host_records(_FakePipeline(), _FakePipeline().recognize(images), rows, rec_boxes)
 
 
 class _FakeTwoPhasePipeline(_FakePipeline):
@@ -65,8 +65,15 @@ class _FakeTwoPhasePipeline(_FakePipeline):
     def records_begin(self, images, rows=None, rec_boxes=128):
         return {"images": images, "rows": rows, "rec_boxes": rec_boxes}
 
-    def records_end(self, state):
-        return D._host_records(_FakePipeline(), state["images"], state["rows"], state["rec_boxes"])
+    def records_counts(self, state):
+        return [len(g) for g in _FakePipeline().recognize(state["images"])]
+
+    def records_end(self, state, rec_boxes=None):
+        return D._host_records(_FakePipeline(), _FakePipeline().recognize(state["images"]), state["rows"],
+                               state["rec_boxes"] if rec_boxes is None else rec_boxes)
+
+    def recognize_records(self, images, rows=None, rec_boxes=128):
+        return self.records_end(self.records_begin(images, rows, rec_boxes))
 
 
 def _stream_worker(rank, world, port, batches, ret, two_phase):
@@ -159,3 +166,70 @@ def test_unpack_blocks_matches_per_block_unpack():
     assert counts.tolist() == [2, 0, 8, 1, 5] == [e[0] for e in expect]
     assert np.array_equal(boxes, np.concatenate([e[1] for e in expect]))
     assert np.array_equal(labels.astype(np.int32), np.concatenate([e[2] for e in expect]))
+
+
+# ---------------------------------------------------------------------------- dense pages: more words than a record holds
+class _DensePipeline(_FakeTwoPhasePipeline):
+    """Image value v -> v words (so one image can exceed any fixed record size)."""
+
+    def recognize(self, images):
+        return [[("w%d" % j, np.full((4, 2), float(j), np.float32)) for j in range(int(im[0, 0, 0]))] for im in images]
+
+    def records_counts(self, state):
+        return [len(g) for g in self.recognize(state["images"])]
+
+    def records_end(self, state, rec_boxes=None):
+        return D._host_records(self, self.recognize(state["images"]), state["rows"],
+                               state["rec_boxes"] if rec_boxes is None else rec_boxes)
+
+
+def _dense_worker(rank, world, port, images, ret, max_boxes, two_phase):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        pipe = _DensePipeline()
+        if not two_phase:                                # duck-typed pipeline: only recognize()
+            pipe = type("P", (), {"detector": _FakeStage(), "recognizer": _FakeStage(), "recognize": _DensePipeline.recognize})()
+        try:
+            res = D.recognize_sharded(pipe, images, max_boxes=max_boxes)
+            out = None if res is None else [[(t, b.tolist()) for t, b in g] for g in res]
+        except D.RecordOverflow as exc:
+            out = "overflow: " + str(exc)
+        if rank == 0:
+            ret.put(out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("max_boxes,two_phase", [(128, True), ("auto", True), ("auto", False)])
+def test_more_words_than_a_record_holds_is_never_silent(max_boxes, two_phase):
+    """An image with more words than ``max_boxes`` (the 128-word cap used to drop words without a signal):
+    a fixed record size makes rank 0 raise RecordOverflow naming the image; ``max_boxes='auto'`` agrees on a record
+    size across the ranks (one all-reduce) and returns every word, as single-GPU ``Pipeline.recognize`` does."""
+    images = np.zeros((4, 4, 4, 3), np.uint8)
+    images[:, 0, 0, 0] = [3, 150, 0, 7]                 # image 1 (rank 0's shard) has 150 words
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    ret = ctx.Queue()
+    procs = [ctx.Process(target=_dense_worker, args=(r, 2, port, images, ret, max_boxes, two_phase)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = ret.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    if max_boxes == "auto":
+        expect = [[(t, b.tolist()) for t, b in g] for g in _DensePipeline().recognize(images)]
+        assert got == expect and len(got[1]) == 150
+    else:
+        assert isinstance(got, str) and "150 words" in got and "max_boxes=128" in got
+
+
+def test_unpack_blocks_overflow_strict_and_capped():
+    boxes = [np.zeros((5, 4, 2), np.float32)]
+    rec = D.pack_records([5], boxes, np.zeros((5, 48), np.int8), 1, 4)
+    with pytest.raises(D.RecordOverflow):
+        D.unpack_blocks([rec], 4)
+    counts, b, l = D.unpack_blocks([rec], 4, strict=False)
+    assert counts.tolist() == [4] and b.shape == (4, 4, 2) and l.shape == (4, 48)

@@ -565,7 +565,9 @@ def test_compact_boxes_and_pack_records_match_host_bookkeeping(ctx, cuda_device)
     scaled = [boxes[i, :held[i]] * inv[i] for i in range(n)]         # tools.adjust_boxes: float32 * float32
     expect = D.pack_records(held, scaled, labels.astype(np.int8), rows, rec_boxes)
     assert np.array_equal(rec.cpu().numpy().view(np.uint32), expect.numpy().view(np.uint32))
-    got_counts, got_boxes, got_labels = D.unpack_blocks([rec], rec_boxes)
+    with pytest.raises(D.RecordOverflow):                            # images 2 and 3 hold 8 words, a record 6: never silent
+        D.unpack_blocks([rec], rec_boxes)
+    got_counts, got_boxes, got_labels = D.unpack_blocks([rec], rec_boxes, strict=False)
     assert got_counts.tolist() == np.minimum(held, rec_boxes).tolist()
 
 
