@@ -40,7 +40,7 @@ class Recognizer:
             checkpoint's ``fc_12`` must have ``len(alphabet) + 1`` classes; if it does not, the reference's
             "backbone weights only" behaviour applies (recognition.py:399-411): the top layer is
             re-initialised (Glorot uniform, zero bias) and has to be trained before it is useful.
-        weights: ``"kurapan"`` looks for ``crnn_kurapan.npz`` (exported) or the reference's ``crnn_kurapan.h5``
+        weights: ``None`` builds an untrained model for ``alphabet`` (as the reference does); ``"kurapan"`` looks for ``crnn_kurapan.npz`` (exported) or the reference's ``crnn_kurapan.h5``
             (read with h5py where installed) in the cache dir; otherwise a ``.npz`` / ``.h5`` path or a dict
             keyed like ``weights.py``.
         build_params: must be ``None`` / the defaults (reference recognition.py:13-23).
@@ -60,6 +60,9 @@ class Recognizer:
         self.device = torch.device("cuda", self.device_index)
         if isinstance(weights, dict):
             tensors = weights
+        elif weights is None:
+            # reference recognition.py:382-383: no weights -> the freshly built (untrained) model for this alphabet
+            tensors = weights_mod.synthetic_crnn_weights(seed=0, alphabet=self.alphabet)
         elif isinstance(weights, str) and weights.endswith(".npz"):
             tensors = weights_mod.load_npz(weights)
         elif isinstance(weights, str) and weights.endswith(".h5"):
@@ -194,6 +197,10 @@ class Recognizer:
         if counts.sum() == 0:
             return [[]] * len(images)
         flat = np.concatenate([np.asarray(b, dtype=np.float32).reshape(-1, 4, 2) for b in box_groups if len(b)])
+        # caller-supplied quads: tools.warpBox first replaces each by its minimum rotated rectangle and divides by its
+        # truncated width / height (tools.py:88-95; ZeroDivisionError for a degenerate box).  Rectangles -- everything
+        # a Detector returns -- pass through bit for bit.
+        flat = tools.rectify_boxes(flat)
         flat_t = torch.from_numpy(np.ascontiguousarray(flat)).to(self.device)
         idx = torch.from_numpy(np.repeat(np.arange(len(counts), dtype=np.int32), counts)).to(self.device)
         crnn_in, _ = self.warp_device(self.gray_device(images_t), flat_t, idx)

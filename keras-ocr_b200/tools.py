@@ -101,3 +101,97 @@ def find_cached(filename, sha256=None, cache_dir=None):
         f"{path} not found and no network is available to download it; pass weights=<dict|path> instead")
     assert sha256 is None or sha256 == sha256sum(path), "Error occurred verifying sha256."
     return path
+
+
+# ----------------------------------------------------------------------------------- box geometry (host)
+def _convex_hull(points):
+    """Counter-clockwise convex hull (Andrew's monotone chain) of (n,2) float64 points, collinear points dropped."""
+    pts = sorted(set(map(tuple, np.asarray(points, dtype=np.float64).tolist())))
+    if len(pts) <= 2:
+        return np.array(pts, dtype=np.float64).reshape(-1, 2)
+
+    def cross(o, a, b):
+        return (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+
+    lower, upper = [], []
+    for p in pts:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], p) <= 0:
+            lower.pop()
+        lower.append(p)
+    for p in reversed(pts):
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], p) <= 0:
+            upper.pop()
+        upper.append(p)
+    return np.array(lower[:-1] + upper[:-1], dtype=np.float64)
+
+
+def minimum_rotated_rectangle(points):
+    """shapely ``MultiPoint(points).minimum_rotated_rectangle`` as the reference uses it (tools.py:544-547), restated:
+    for every edge of the convex hull, the axis-parallel bounding rectangle in that edge's frame; the one of least
+    area, transformed back.  Returns (4,2) float64, or None when the hull has no area (shapely then returns a point
+    or a line, ``.exterior`` raises AttributeError and the reference falls back to the raw points, tools.py:548-550).
+    shapely is not installable offline, so this follows its published algorithm (PARITY UNPINNED beyond that)."""
+    hull = _convex_hull(points)
+    if len(hull) < 3:
+        return None
+    best, best_area = None, None
+    for i in range(len(hull)):
+        dx, dy = hull[(i + 1) % len(hull)] - hull[i]
+        length = float(np.hypot(dx, dy))
+        ux, uy = dx / length, dy / length
+        vx, vy = -uy, ux
+        a, b = hull @ np.array([ux, uy]), hull @ np.array([vx, vy])          # coordinates in the edge's frame
+        area = (a.max() - a.min()) * (b.max() - b.min())
+        if best_area is None or area < best_area:
+            corners = np.array([[a.min(), b.min()], [a.max(), b.min()], [a.max(), b.max()], [a.min(), b.max()]])
+            best = corners @ np.array([[ux, uy], [vx, vy]])                  # back to image coordinates
+            best_area = area
+    return best
+
+
+def get_rotated_box(points):
+    """tools.get_rotated_box (reference tools.py:533-581): minimum rotated rectangle of the points, corners ordered
+    top-left, top-right, bottom-right, bottom-left (the imutils rule), float32, plus the rotation angle."""
+    points = np.asarray(points)
+    pts = minimum_rotated_rectangle(points)
+    if pts is None:
+        pts = points
+    x_sorted = pts[np.argsort(pts[:, 0]), :]
+    left, right = x_sorted[:2, :], x_sorted[2:, :]
+    tl, bl = left[np.argsort(left[:, 1]), :]
+    d = np.sqrt(((right - tl[np.newaxis]) ** 2).sum(1))
+    br, tr = right[np.argsort(d)[::-1], :]
+    out = np.array([tl, tr, br, bl], dtype="float32")
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rotation = np.arctan((tl[0] - bl[0]) / (tl[1] - bl[1]))
+    return out, rotation
+
+
+def get_rotated_width_height(box):
+    """tools.get_rotated_width_height (reference tools.py:41-57): truncated mean lengths of opposite sides."""
+    box = np.asarray(box, dtype=np.float64)
+
+    def dist(a, b):
+        return float(np.sqrt(((box[a] - box[b]) ** 2).sum()))
+
+    return int((dist(0, 1) + dist(2, 3)) / 2), int((dist(0, 3) + dist(1, 2)) / 2)
+
+
+def rectify_boxes(boxes, tolerance=1e-3):
+    """What ``tools.warpBox`` does to a caller-supplied quad before it builds the homography (reference
+    tools.py:88-95): replace it by its minimum rotated rectangle and measure that rectangle.  A quad that already IS
+    a rectangle (every corner within ``tolerance`` px of the rectified one -- everything ``getBoxes`` emits) is kept
+    bit for bit, so boxes that come from the detector are not perturbed by the fp64 round trip.  Raises
+    ZeroDivisionError for a box whose width or height truncates to 0, as the reference does (tools.py:95).
+    boxes: (n,4,2) -> (n,4,2) float32."""
+    boxes = np.asarray(boxes, dtype=np.float32).reshape(-1, 4, 2)
+    out = boxes.copy()
+    for k, quad in enumerate(boxes):
+        rect, _ = get_rotated_box(quad)
+        w, h = get_rotated_width_height(rect)
+        if w == 0 or h == 0:
+            raise ZeroDivisionError("division by zero")          # scale = min(target_width / w, target_height / h)
+        nearest = np.abs(rect[:, None, :] - quad[None, :, :]).max(-1).min(-1)      # each rectified corner vs the quad's
+        if nearest.max() > tolerance:
+            out[k] = rect
+    return out

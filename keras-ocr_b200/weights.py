@@ -232,15 +232,12 @@ def map_keras_datasets(flat):
 
 
 def load_keras_h5(path):
-    """Read the reference's ``crnn_kurapan.h5`` / ``crnn_kurapan_notop.h5`` (recognition.py:27-44).  Needs h5py,
-    which this offline image does not have: export to ``.npz`` once where it is available."""
-    try:
-        import h5py
-    except ImportError as exc:
-        raise ImportError("reading Keras .h5 weights needs h5py; export them to .npz once with "
-                          "keras_ocr_b200.weights.load_keras_h5 + numpy.savez on a machine that has it") from exc
-    flat = {}
-    with h5py.File(path, "r") as f:
-        root = f["model_weights"] if "model_weights" in f else f
-        root.visititems(lambda name, obj: flat.__setitem__(name, np.array(obj)) if isinstance(obj, h5py.Dataset) else None)
+    """Read the reference's ``crnn_kurapan.h5`` / ``crnn_kurapan_notop.h5`` (recognition.py:27-44; loaded there by
+    ``model.load_weights``, 386-392) with this package's own HDF5 reader (``hdf5.py``; no h5py needed).  Both Keras
+    layouts are accepted: ``save_weights`` (layer groups at the root) and ``model.save`` (under ``model_weights``)."""
+    from . import hdf5
+
+    flat = hdf5.read_datasets(path)
+    if any(k.startswith("model_weights/") for k in flat):
+        flat = {k[len("model_weights/"):]: v for k, v in flat.items() if k.startswith("model_weights/")}
     return map_keras_datasets(flat)

@@ -109,13 +109,58 @@ def get_boxes(y_pred, **thresholds):
 
 
 # ----------------------------------------------------------------------------- warpBox
-def order_corners(points):
-    """get_rotated_box, reference tools.py:533-581, on its no-shapely branch (548-550).
+def min_rotated_rectangle(points):
+    """shapely's ``MultiPoint(points).minimum_rotated_rectangle.exterior`` minus its closing point (reference
+    tools.py:544-547), restated from shapely's published algorithm (shapely/geometry/base.py, the pure-Python
+    ``oriented_envelope``): convex hull; for every hull edge rotate the hull into the edge's frame and take the
+    axis-parallel envelope; keep the envelope of least area and rotate it back.  Returns None when the hull is a point
+    or a segment (shapely returns a geometry without ``.exterior`` -> the reference's AttributeError branch).
+    shapely is absent offline: PARITY UNPINNED for this function (getBoxes only emits rectangles, on which it is the
+    identity up to fp64 rounding -- ``order_corners`` keeps those bit for bit)."""
+    import math
+    pts = sorted({(float(x), float(y)) for x, y in np.asarray(points, dtype=np.float64)})
+    if len(pts) < 3:
+        return None
+    cross = lambda o, a, b: (a[0] - o[0]) * (b[1] - o[1]) - (a[1] - o[1]) * (b[0] - o[0])
+    lower, upper = [], []
+    for q in pts:
+        while len(lower) >= 2 and cross(lower[-2], lower[-1], q) <= 0:
+            lower.pop()
+        lower.append(q)
+    for q in reversed(pts):
+        while len(upper) >= 2 and cross(upper[-2], upper[-1], q) <= 0:
+            upper.pop()
+        upper.append(q)
+    hull = lower[:-1] + upper[:-1]
+    if len(hull) < 3:
+        return None
+    best = None
+    for (x1, y1), (x2, y2) in zip(hull, hull[1:] + hull[:1]):
+        length = math.sqrt((x2 - x1) ** 2 + (y2 - y1) ** 2)
+        ux, uy = (x2 - x1) / length, (y2 - y1) / length
+        vx, vy = -uy, ux
+        xs = [ux * x + uy * y for x, y in hull]
+        ys = [vx * x + vy * y for x, y in hull]
+        area = (max(xs) - min(xs)) * (max(ys) - min(ys))
+        if best is None or area < best[0]:
+            env = [(min(xs), min(ys)), (max(xs), min(ys)), (max(xs), max(ys)), (min(xs), max(ys))]
+            best = (area, [(ux * a + vx * b, uy * a + vy * b) for a, b in env])
+    return np.array(best[1], dtype=np.float64)
 
-    shapely's minimum_rotated_rectangle is the identity on a 4-corner rectangle, which is all
-    getBoxes emits; then the imutils ordering: tl, tr, br, bl.
+
+def order_corners(points):
+    """get_rotated_box, reference tools.py:533-581: minimum rotated rectangle (``min_rotated_rectangle``; the raw
+    points on the reference's AttributeError branch, 548-550), then the imutils ordering tl, tr, br, bl.
+
+    A 4-corner rectangle -- all that getBoxes emits -- is its own minimum rotated rectangle; it is kept bit for bit
+    (corners within 1e-3 px) so that the fp64 round trip cannot move a float32 coordinate by an ulp.
     """
     pts = np.asarray(points)
+    rect = min_rotated_rectangle(pts)
+    if rect is not None:
+        near = np.abs(rect[:, None, :] - pts[None, :, :].astype(np.float64)).max(-1).min(-1)
+        if near.max() > 1e-3:
+            pts = rect
     by_x = pts[np.argsort(pts[:, 0]), :]
     left, right = by_x[:2], by_x[2:]
     left = left[np.argsort(left[:, 1]), :]
