@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 
 #include "common.cuh"
@@ -115,29 +116,76 @@ struct CraftPlan {
       off_h2, off_h3, off_x16, bytes;
 };
 
+// Liveness-based packing: every buffer lives from the launch that first writes it to the launch that last reads it
+// (the forward pass is one stream-ordered chain of launches, see b2o_craft_forward: the step numbers below are its
+// launch order); buffers whose lifetimes do not overlap share memory.  Greedy by size: largest first, each at the
+// lowest offset that is free for its whole lifetime.  32 x 1536 x 1536: 21.8 GB instead of 41 GB with every buffer
+// live (the peak is the two full-resolution 64-channel maps around slice1.3), and 73 -> 39 GB at max_size 2048.
 CraftPlan plan_craft(int n, int h, int w) {
   CraftPlan p;
   p.n = n; p.h1 = h; p.w1 = w;
   p.h2 = h / 2; p.w2 = w / 2; p.h4 = p.h2 / 2; p.w4 = p.w2 / 2;
   p.h8 = p.h4 / 2; p.w8 = p.w4 / 2; p.h16 = p.h8 / 2; p.w16 = p.w8 / 2;
-  size_t off = 0;
-  auto take = [&](int hh, int ww, int c) {
-    const size_t r = off;
-    off += (static_cast<size_t>(n) * hh * ww * c * 2 + 255) / 256 * 256;
-    return r;
+  struct Buf { size_t* off; size_t bytes; int first, last; };
+  std::vector<Buf> bufs;
+  auto take = [&](size_t* off, int hh, int ww, int c, int first, int last) {
+    bufs.push_back({off, (static_cast<size_t>(n) * hh * ww * c * 2 + 255) / 256 * 256, first, last});
   };
-  p.off_a = take(p.h1, p.w1, 64); p.off_b = take(p.h1, p.w1, 64); p.off_p1 = take(p.h2, p.w2, 64);
-  p.off_c = take(p.h2, p.w2, 128); p.off_cat4 = take(p.h2, p.w2, 192); p.off_p2 = take(p.h4, p.w4, 128);
-  p.off_d = take(p.h4, p.w4, 256); p.off_cat3 = take(p.h4, p.w4, 384); p.off_e = take(p.h4, p.w4, 256);
-  p.off_p3 = take(p.h8, p.w8, 256); p.off_f = take(p.h8, p.w8, 512); p.off_cat2 = take(p.h8, p.w8, 768);
-  p.off_g = take(p.h8, p.w8, 512); p.off_p4 = take(p.h16, p.w16, 512); p.off_hh = take(p.h16, p.w16, 512);
-  p.off_cat1 = take(p.h16, p.w16, 1536); p.off_mp = take(p.h16, p.w16, 512); p.off_s5a = take(p.h16, p.w16, 1024);
-  p.off_u1a = take(p.h16, p.w16, 512); p.off_u1b = take(p.h16, p.w16, 256); p.off_u2a = take(p.h8, p.w8, 256);
-  p.off_u2b = take(p.h8, p.w8, 128); p.off_u3a = take(p.h4, p.w4, 128); p.off_u3b = take(p.h4, p.w4, 64);
-  p.off_u4a = take(p.h2, p.w2, 64); p.off_u4b = take(p.h2, p.w2, 32); p.off_h1 = take(p.h2, p.w2, 32);
-  p.off_h2 = take(p.h2, p.w2, 32); p.off_h3 = take(p.h2, p.w2, 16);
-  p.off_x16 = take(p.h1, p.w1, 16);       // normalised input, 3 -> 16 channels, for the tensor-core stem
-  p.bytes = off;
+  // step: 0 normalize16, 1 stem, 2 slice1.3, 3 slice1.7, 4 slice1.10, 5 slice2.14, 6 slice2.17, 7 slice3.20, 8 slice3.24,
+  // 9 slice3.27, 10 slice4.30, 11 slice4.34, 12 slice4.37, 13 maxpool3, 14 slice5.1, 15 slice5.2, 16 upconv1.0,
+  // 17 upconv1.3, 18 upsample, 19 upconv2.0, 20 upconv2.3, 21 upsample, 22 upconv3.0, 23 upconv3.3, 24 upsample,
+  // 25 upconv4.0, 26 upconv4.3, 27 conv_cls.0, 28 conv_cls.2, 29 conv_cls.4 (+ fused tail), 30 head_tail
+  take(&p.off_x16, p.h1, p.w1, 16, 0, 1);          // normalised input, 3 -> 16 channels, for the tensor-core stem
+  take(&p.off_a, p.h1, p.w1, 64, 1, 2);
+  take(&p.off_b, p.h1, p.w1, 64, 2, 2);            // full-resolution conv output: only written when the pool is not fused
+  take(&p.off_p1, p.h2, p.w2, 64, 2, 3);
+  take(&p.off_c, p.h2, p.w2, 128, 3, 4);
+  take(&p.off_cat4, p.h2, p.w2, 192, 4, 25);       // [upsampled decoder | tap s1]: written at 4 and 24, read at 25
+  take(&p.off_p2, p.h4, p.w4, 128, 4, 5);
+  take(&p.off_d, p.h4, p.w4, 256, 5, 6);
+  take(&p.off_cat3, p.h4, p.w4, 384, 6, 22);
+  take(&p.off_e, p.h4, p.w4, 256, 7, 7);
+  take(&p.off_p3, p.h8, p.w8, 256, 7, 8);
+  take(&p.off_f, p.h8, p.w8, 512, 8, 9);
+  take(&p.off_cat2, p.h8, p.w8, 768, 9, 19);
+  take(&p.off_g, p.h8, p.w8, 512, 10, 10);
+  take(&p.off_p4, p.h16, p.w16, 512, 10, 11);
+  take(&p.off_hh, p.h16, p.w16, 512, 11, 12);
+  take(&p.off_cat1, p.h16, p.w16, 1536, 12, 16);
+  take(&p.off_mp, p.h16, p.w16, 512, 13, 14);
+  take(&p.off_s5a, p.h16, p.w16, 1024, 14, 15);
+  take(&p.off_u1a, p.h16, p.w16, 512, 16, 17);
+  take(&p.off_u1b, p.h16, p.w16, 256, 17, 18);
+  take(&p.off_u2a, p.h8, p.w8, 256, 19, 20);
+  take(&p.off_u2b, p.h8, p.w8, 128, 20, 21);
+  take(&p.off_u3a, p.h4, p.w4, 128, 22, 23);
+  take(&p.off_u3b, p.h4, p.w4, 64, 23, 24);
+  take(&p.off_u4a, p.h2, p.w2, 64, 25, 26);
+  take(&p.off_u4b, p.h2, p.w2, 32, 26, 27);
+  take(&p.off_h1, p.h2, p.w2, 32, 27, 28);
+  take(&p.off_h2, p.h2, p.w2, 32, 28, 29);
+  take(&p.off_h3, p.h2, p.w2, 16, 29, 30);
+  std::vector<int> order(bufs.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bufs[a].bytes > bufs[b].bytes; });
+  std::vector<int> placed;
+  size_t total = 0;
+  for (int i : order) {
+    // candidate offsets: 0 and the end of every placed buffer that is live at the same time
+    std::vector<std::pair<size_t, size_t>> busy;      // [begin, end) of time-overlapping placed buffers
+    for (int j : placed)
+      if (bufs[j].first <= bufs[i].last && bufs[i].first <= bufs[j].last) busy.push_back({*bufs[j].off, *bufs[j].off + bufs[j].bytes});
+    std::sort(busy.begin(), busy.end());
+    size_t at = 0;
+    for (const auto& b : busy) {
+      if (at + bufs[i].bytes <= b.first) break;
+      if (b.second > at) at = b.second;
+    }
+    *bufs[i].off = at;
+    placed.push_back(i);
+    if (at + bufs[i].bytes > total) total = at + bufs[i].bytes;
+  }
+  p.bytes = total;
   return p;
 }
 
@@ -190,6 +238,7 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : (atoi(e) == 1 ? 1 : 0);
   if (const char* e = getenv("B2O_TC_BOX16")) ctx->tc_box16 = atoi(e) != 0;
+  if (const char* e = getenv("B2O_FUSED_TAIL")) ctx->no_fused_tail = atoi(e) == 0;      // 0: separate head_tail_kernel (A/B, tests)
   if (const char* e = getenv("B2O_TC_PAIR")) {        // default 1; 0 = single-CTA tiles (A/B runs); 2 = generic tiles too
     ctx->tc_pair = atoi(e) != 0;
     ctx->tc_pair_generic = atoi(e) == 2;
@@ -479,8 +528,15 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
   // head (392-410)
   B2O_RETURN_IF(conv_run(ctx, L("conv_cls.0"), u4b, h1, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("conv_cls.2"), h1, h2, 0, st));
-  B2O_RETURN_IF(conv_run(ctx, L("conv_cls.4"), h2, h3, 0, st));
-  B2O_RETURN_IF(head_tail_run(ctx, L("conv_cls.6"), L("conv_cls.8"), h3, scores, st));
+  if (ctx->conv_engine == B2O_CONV_AUTO && L("conv_cls.4").block_n == 16 && !ctx->no_fused_tail) {
+    // conv_cls.6 + conv_cls.8 ride in conv_cls.4's epilogue (same arithmetic as head_tail_kernel, bit for bit):
+    // one launch and the 16-channel map's round trip through HBM less
+    const ConvTail tail = {L("conv_cls.6").w_simt, L("conv_cls.6").t1, L("conv_cls.8").w_simt, L("conv_cls.8").t1, scores};
+    B2O_RETURN_IF(conv_tc_run(ctx, L("conv_cls.4"), h2, h3, 0, st, nullptr, 1, &tail));
+  } else {
+    B2O_RETURN_IF(conv_run(ctx, L("conv_cls.4"), h2, h3, 0, st));
+    B2O_RETURN_IF(head_tail_run(ctx, L("conv_cls.6"), L("conv_cls.8"), h3, scores, st));
+  }
   return B2O_OK;
 }
 

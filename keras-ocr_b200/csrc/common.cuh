@@ -88,8 +88,9 @@ struct b2o_ctx {
   int conv_engine = B2O_CONV_AUTO;
   int tc_issuers = 0;          // MMA-issuing warps of conv_tc_kernel: 0 = auto (2 for N <= 128 tiles), 1, 2
   bool tc_pair = true;         // CTA pairs (tcgen05 cta_group::2) for the halo-tile layers; B2O_TC_PAIR=0 turns them off
-  bool tc_box16 = false;       // B2O_TC_BOX16=1: one 16 x 18 A box per K chunk in MODE 3 layers -- not yet GPU-validated
-  bool tc_pair_generic = false;   // B2O_TC_PAIR=2: also pair the generic tiles (1x1 / dilated layers) -- not yet GPU-validated
+  bool tc_box16 = true;        // one 16 x 18 A box per K chunk in MODE 3 layers (B2O_TC_BOX16=0: three 8 x 18 boxes)
+  bool tc_pair_generic = false;   // B2O_TC_PAIR=2: also pair the generic tiles (1x1 / dilated layers): bit-identical, no gain measured (profiles/r2a_ab_pair2.log)
+  bool no_fused_tail = false;  // B2O_FUSED_TAIL=0: conv_cls.6/.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue
   std::set<const void*> configured;   // kernels whose per-device launch attributes are set on this device
   int64_t launches = 0;
   std::string error;
@@ -110,11 +111,19 @@ struct b2o_ctx {
   void set_error(const std::string& e) { error = e; }
 };
 
+// CRAFT tail fused into the epilogue of a 16-channel tensor-core layer: conv_cls.6 (1x1 16->16, ReLU) and conv_cls.8
+// (1x1 16->2) on the 16 channels a thread already holds; fp32 (text, link) scores out (detection.py:404-410).
+struct ConvTail {
+  const float *w6, *b6, *w8, *b8;   // [cin 16][cout 16] fp32 (fp16-rounded values), [16], [16][2], [2]
+  float* scores;                    // (n,h,w,2)
+};
+
 // ---- engines (conv_tc.cu, conv_simt.cu) -------------------------------------------------------
 int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L);   // builds wmap / picks block_n (0 if ineligible)
 // pool_out != null: also write the 2x2/2 max-pooled output (fused epilogue); write_full = 0 skips `out`
 int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
-                int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1);
+                int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1,
+                const ConvTail* tail = nullptr);
 int conv_simt_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
                   int out_f32, cudaStream_t st);
 int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,

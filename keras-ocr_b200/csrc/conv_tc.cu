@@ -71,7 +71,12 @@ struct TcParams {
   __half* pool_out;                       // fused 2x2/2 max-pool output (or null)
   int pool_ld, PH, PW;
   int box16;                              // MODE 3 with ONE 16 x 18 A box per K chunk (dx taps through the descriptor)
+  // fused CRAFT tail (16-channel layers only): conv_cls.6 (1x1 16->16 ReLU) + conv_cls.8 (1x1 16->2) applied to the
+  // epilogue's 16 channels in registers, fp32 (text, link) scores out -- detection.py:404-410
+  const float *tail_w6, *tail_b6, *tail_w8, *tail_b8;   // [16][16], [16], [16][2], [2]
+  float* tail_out;                        // (N,H,W,2) fp32, or null
 };
+constexpr int TAIL_FLOATS = 256 + 16 + 32 + 2;
 
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -346,17 +351,17 @@ __device__ __forceinline__ void epi_pool8(uint32_t* pk) {
 //       and the filter bank is fetched from L2 once per 256 pixels instead of once per 128.  Validated and on by
 //       default for the halo modes; generic tiles (MODE 0: 1x1 and dilated layers) pair the same way but are opt-in
 //       (B2O_TC_PAIR=2) until they have run on a GPU.
-// BOX16 (MODE 3 only, opt-in B2O_TC_BOX16=1, NOT yet validated on a GPU -- scripts/probes/dx_shift_probe.cu tests the
+// BOX16 (MODE 3 only; the default there, B2O_TC_BOX16=0 turns it off; scripts/probes/dx_shift_probe.cu tests the
 //       descriptor semantics it relies on): ONE 16 x 18-pixel A box per K chunk serves all nine taps.  The dy taps
 //       move the A descriptor by whole image rows (2 KB = the stride between 8-row groups), the dx taps by single
-//       128-byte pixel rows inside a swizzle atom, with the descriptor's base offset set to dx.  2.25x instead of
+//       pixel rows (KCH * 2 bytes) inside a swizzle atom, descriptor base offset 0.  2.25x instead of
 //       3.375x of the tile's input crosses L2->SM, in one TMA instruction instead of three and 36 KB instead of 55 KB.
 //       The MMAs are issued in the same (dx, chunk, dy, k) order as without it.
 template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                const TcParams p) {
-  static_assert(!BOX16 || (MODE == 3 && KCH == 64), "the single-box tile is implemented for grouped tiles, 64-channel chunks");
+  static_assert(!BOX16 || MODE == 3, "the single-box tile is implemented for grouped tiles (whole tile on one barrier)");
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // filter rows staged by one CTA
   constexpr int B_BYTES = B_ROWS * KCH * 2;
   const uint32_t rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader
@@ -400,6 +405,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       aff[p.cout + i] = p.t1[i];
       if (p.s2 != nullptr) { aff[2 * p.cout + i] = p.s2[i]; aff[3 * p.cout + i] = p.t2[i]; }
     }
+  }
+  // fused tail constants behind the affine ones: [w6 | b6 | w8 | b8]
+  float* const tail_s = aff + 4 * p.cout;
+  if (BLOCK_N == 16 && p.tail_out != nullptr) {
+    for (int i = threadIdx.x; i < TAIL_FLOATS; i += NUM_THREADS)
+      tail_s[i] = i < 256 ? p.tail_w6[i] : (i < 272 ? p.tail_b6[i - 256] : (i < 304 ? p.tail_w8[i - 272] : p.tail_b8[i - 304]));
   }
   const float* const e_s1 = p.aff_smem ? aff : p.s1;
   const float* const e_t1 = p.aff_smem ? aff + p.cout : p.t1;
@@ -573,8 +584,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         if (elect_one()) {
           uint64_t adesc = a_desc0 + static_cast<uint64_t>(static_cast<uint32_t>(sa * p.group) * a_step);
           uint32_t accumulate = 0;
-          // BOX16: dx = one 128-byte pixel row further into the same stages, descriptor base offset (bits 49-51) = dx
-          constexpr uint64_t DX_STEP = (static_cast<uint64_t>(1) << 49) | static_cast<uint64_t>((KCH * 2) >> 4);
+          // BOX16: dx = one 128-byte pixel row further into the same stages.  The descriptor's base-offset field stays 0:
+          // the swizzle pattern is a function of the absolute shared-memory address bits, so a start address that is not
+          // 1 KB-aligned needs no correction (scripts/probes/dx_shift_probe.cu on B200: offset 0 right for all nine taps,
+          // offset = dx wrong for dx = 1, 2 -- profiles/r2_dx_shift_probe.log)
+          constexpr uint64_t DX_STEP = static_cast<uint64_t>((KCH * 2) >> 4);
           const uint64_t adesc_tile = adesc;
           for (int g = 0; g < 3; ++g) {
             if (BOX16) adesc = adesc_tile + static_cast<uint64_t>(g) * DX_STEP;
@@ -697,6 +711,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
         const int c0 = c_base + ch * CH;
         float y[CH];
         epi_affine(p, e_s1, e_t1, e_s2, e_t2, v, c0, y);
+        if (BLOCK_N == 16 && p.tail_out != nullptr) {        // warp-uniform; only the 16-channel instances carry it
+          // The unfused path stores these 16 channels as fp16 and head_tail_kernel reads them back: round the same way
+          // and run the same fmaf chains, so the scores are bit-identical to conv_cls.4 -> head_tail_kernel.
+          float x[CH];
+#pragma unroll
+          for (int j = 0; j < CH; ++j) x[j] = __half2float(__float2half_rn(y[j]));
+          float o0 = tail_s[304], o1 = tail_s[305];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float a = tail_s[256 + j];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) a = fmaf(x[c], tail_s[c * 16 + j], a);
+            a = fmaxf(a, 0.0f);
+            o0 = fmaf(a, tail_s[272 + j * 2 + 0], o0);
+            o1 = fmaf(a, tail_s[272 + j * 2 + 1], o1);
+          }
+          if (valid) reinterpret_cast<float2*>(p.tail_out)[pix] = make_float2(o0, o1);
+          return;
+        }
         if (p.out_f32) {
           if (valid) {
             float* o = reinterpret_cast<float*>(p.out) + pix * p.out_ld + c0;
@@ -926,7 +959,11 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
 }
 
 int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out, int out_f32,
-                cudaStream_t st, const TensorView* pool_out, int write_full) {
+                cudaStream_t st, const TensorView* pool_out, int write_full, const ConvTail* tail) {
+  if (tail != nullptr && (L.block_n != 16 || L.cout != 16 || pool_out != nullptr)) {
+    ctx->set_error("conv_tc_run: the fused tail needs a 16-channel layer (" + L.name + ")");
+    return B2O_ERR_ARG;
+  }
   if (L.block_n == 0) { ctx->set_error("conv_tc_run: layer " + L.name + " not eligible"); return B2O_ERR_ARG; }
   if (in.c != L.cin || out.c != L.cout || in.n != out.n || in.h != out.h || in.w != out.w) {
     ctx->set_error("conv_tc_run: shape mismatch in " + L.name);
@@ -979,7 +1016,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   // layers with few output channels keep their epilogue constants (s1,t1,s2,t2) in shared memory: their
   // epilogue is latency-bound and the per-chunk __ldg's of the constants were its top stall (ncu source view)
   p.aff_smem = L.cout <= 256 ? 1 : 0;
-  const int aff_bytes = p.aff_smem ? 4 * L.cout * 4 : 0;
+  const int aff_bytes = (p.aff_smem ? 4 * L.cout * 4 : 0) + (tail ? TAIL_FLOATS * 4 : 0);
   const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/ - aff_bytes;
   p.a_bytes = p.halo ? 18 * 8 * kch * 2 : 128 * kch * 2;
   p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
@@ -987,10 +1024,10 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   // (the leader's barrier counts both CTAs' halves of a pair: the mbarrier tx-count holds 2^20 - 1 bytes)
   p.resident = (p.halo && p.n_tiles == 1 && res_bytes + 2LL * p.a_stride <= budget &&
                 res_bytes * (pair ? 2 : 1) <= (1 << 20) - 1) ? 1 : 0;
-  // opt-in (B2O_TC_BOX16=1, not GPU-validated): one 16-pixel-wide box per K chunk instead of three 8-pixel-wide ones,
-  // where the layer then still runs as whole tiles per barrier (MODE 3)
-  if (ctx->tc_box16 && p.resident && kch == 64 && (bn == 64 || bn == 128) && ctx->conv_engine == B2O_CONV_AUTO) {
-    const int a16 = 18 * 16 * kch * 2;                     // 36864 B: a whole number of 1 KB swizzle atoms
+  // single-box tiles (default; B2O_TC_BOX16=0 restores three 8-pixel-wide boxes per K chunk): one 16-pixel-wide box per
+  // K chunk, where the layer then still runs as whole tiles per barrier (MODE 3).  Same MMA order, bit-identical results.
+  if (ctx->tc_box16 && p.resident && bn <= 128 && ctx->conv_engine == B2O_CONV_AUTO) {
+    const int a16 = 18 * 16 * kch * 2;                     // 36864 / 18432 / 9216 B: whole 1 KB units for every swizzle mode
     if ((budget - res_bytes) / a16 >= 2 * kchunks) { p.box16 = 1; p.a_bytes = a16; p.a_stride = a16; }
   }
   if (p.resident) {
@@ -1029,6 +1066,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;    // one CTA per SM (TMEM base 0, see kernel)
 
   p.s1 = L.s1; p.t1 = L.t1; p.s2 = L.s2; p.t2 = L.t2; p.relu = L.relu;
+  if (tail) { p.tail_w6 = tail->w6; p.tail_b6 = tail->b6; p.tail_w8 = tail->w8; p.tail_b8 = tail->b8; p.tail_out = tail->scores; }
   p.out = out.ptr; p.out_ld = out.ld; p.out_f32 = out_f32; p.write_full = write_full;
   if (want_pool) {
     if (out_f32 || pool_out->c != L.cout || pool_out->h != in.h / 2 || pool_out->w != in.w / 2 || (pool_out->ld % 8)) {
@@ -1059,21 +1097,26 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
                    std::to_string(static_cast<int>(r)));
     return B2O_ERR_CUDA;
   }
-#define B2O_TC_BOX16_CASE(BN)                                                                          \
-  if (p.box16 && p.group && bn == BN) {                                                               \
-    const int rc = pair ? launch<BN, 64, 3, true, true>(ctx, amap, L, p, smem_bytes, st)              \
-                        : launch<BN, 64, 3, false, true>(ctx, amap, L, p, smem_bytes, st);            \
-    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full) : rc; \
+#define B2O_TC_BOX16_PAIR_CASE(BN)                                                                     \
+  if (p.box16 && p.group && pair && bn == BN) {                                                       \
+    const int rc = launch<BN, 64, 3, true, true>(ctx, amap, L, p, smem_bytes, st);                    \
+    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full, tail) : rc; \
   }
-  B2O_TC_BOX16_CASE(64); B2O_TC_BOX16_CASE(128);
+  B2O_TC_BOX16_PAIR_CASE(64); B2O_TC_BOX16_PAIR_CASE(128);
+#undef B2O_TC_BOX16_PAIR_CASE
+#define B2O_TC_BOX16_CASE(BN, KC)                                                                      \
+  if (p.box16 && p.group && !pair && bn == BN && kch == KC) return launch<BN, KC, 3, false, true>(ctx, amap, L, p, smem_bytes, st);
+  B2O_TC_BOX16_CASE(16, 64); B2O_TC_BOX16_CASE(32, 64); B2O_TC_BOX16_CASE(64, 64); B2O_TC_BOX16_CASE(128, 64);
+  B2O_TC_BOX16_CASE(16, 32); B2O_TC_BOX16_CASE(32, 32); B2O_TC_BOX16_CASE(32, 16); B2O_TC_BOX16_CASE(64, 16);
 #undef B2O_TC_BOX16_CASE
+  if (p.box16 && p.group) { ctx->set_error("conv_tc_run: no single-box kernel instance for " + L.name); return B2O_ERR_ARG; }
 #define B2O_TC_PAIR_CASE(BN)                                                                  \
   if (pair && bn == BN) {                                                                     \
     const int rc = (p.resident && p.group) ? launch<BN, 64, 3, true>(ctx, amap, L, p, smem_bytes, st) \
                    : p.resident            ? launch<BN, 64, 2, true>(ctx, amap, L, p, smem_bytes, st) \
                    : p.halo                ? launch<BN, 64, 1, true>(ctx, amap, L, p, smem_bytes, st) \
                                            : launch<BN, 64, 0, true>(ctx, amap, L, p, smem_bytes, st); \
-    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full) : rc; \
+    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full, tail) : rc; \
   }
   B2O_TC_PAIR_CASE(64); B2O_TC_PAIR_CASE(128); B2O_TC_PAIR_CASE(256);
 #undef B2O_TC_PAIR_CASE

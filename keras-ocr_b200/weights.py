@@ -143,8 +143,29 @@ def synthetic_craft_weights(seed=0, textlike=False):
     return w
 
 
-def synthetic_crnn_weights(seed=1, alphabet=ALPHABET):
-    """Seeded CRNN weights keyed by Keras layer name (Keras layouts); the top layer has len(alphabet)+1 classes."""
+HERSHEY_HEAD = "crnn_hershey_head.npz"      # keras-ocr_b200/data/: fc_9 + BiLSTM + fc_12 fitted on rendered words (see below)
+HERSHEY_SEED = 2                            # the backbone seed that head was fitted on
+
+
+def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False):
+    """Seeded CRNN weights keyed by Keras layer name (Keras layouts); the top layer has len(alphabet)+1 classes.
+
+    ``decisive=True`` (seed 2, default alphabet only): the convolutional backbone and the spatial transformer keep their
+    seeded random weights, and everything after the transformer -- ``fc_9``, the four LSTMs, ``fc_12`` -- comes from
+    ``data/crnn_hershey_head.npz``, fitted with CTC loss on the crops the oracle pipeline cuts out of
+    ``oracle.synth.text_images`` pages (``oracle/train_crnn_head.py``; cv2's Hershey font, no pretrained file involved).
+    That recognizer READS the synthetic pages: its per-step argmax is decided by a wide margin, so decoded strings can be
+    compared for identity (BASELINE.json north_star) instead of up to the near-ties random weights leave."""
+    if decisive:
+        import os
+        assert seed == HERSHEY_SEED and alphabet == ALPHABET, "the fitted head belongs to seed 2 / the default alphabet"
+        w = synthetic_crnn_weights(seed, alphabet)
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", HERSHEY_HEAD)
+        with np.load(path) as head:
+            for k in head.files:
+                assert k in w and w[k].shape == head[k].shape, k
+                w[k] = head[k].astype(np.float32)
+        return w
     rng = np.random.default_rng(seed)
     w = {}
     for name, cin, cout, k, bn in CRNN_CONVS:

@@ -676,12 +676,14 @@ def test_cta_pairs_give_bit_identical_results(cuda_device, monkeypatch):
     assert torch.equal(logits[0][0], logits[1][0]) and torch.equal(logits[0][1], logits[1][1])
 
 
-@pytest.mark.skipif(os.environ.get("B2O_EXPERIMENTAL") != "1",
-                    reason="opt-in kernel variants that have not run on a GPU yet: B2O_EXPERIMENTAL=1 pytest -m gpu -k experimental")
-@pytest.mark.parametrize("switch", [("B2O_TC_BOX16", "1"), ("B2O_TC_PAIR", "2")], ids=["box16", "generic_pairs"])
-def test_experimental_conv_variants_are_bit_identical(cuda_device, monkeypatch, switch):
-    """The opt-in convolution variants (one 16 x 18 A box per K chunk; CTA pairs on generic tiles) keep the MMA order of
-    the default path, so CRAFT score maps and CRNN logits must not change by a bit."""
+@pytest.mark.parametrize("switch", [("B2O_TC_BOX16", "0"), ("B2O_TC_PAIR", "2"), ("B2O_FUSED_TAIL", "0")],
+                         ids=["three_boxes_vs_single_box", "generic_pairs", "separate_head_tail"])
+def test_conv_variants_are_bit_identical(cuda_device, monkeypatch, switch):
+    """Kernel variants that keep the MMA / fmaf order of the default path must not change a bit of the CRAFT score
+    maps or the CRNN logits:  B2O_TC_BOX16=0 -- three 8 x 18 A boxes per K chunk instead of the default single 16 x 18
+    box (dx taps through the descriptor start address);  B2O_TC_PAIR=2 -- CTA pairs on the generic tiles too;
+    B2O_FUSED_TAIL=0 -- conv_cls.6 / conv_cls.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue.
+    Sizes: odd tile columns (200 / 8 = 25), several tiles per CTA, and the 768 x 768 case of BASELINE configs[1]."""
     from keras_ocr_b200.detection import Detector
     from keras_ocr_b200.recognition import Recognizer
     cw, rw = W.synthetic_craft_weights(3), W.synthetic_crnn_weights(2)
