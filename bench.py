@@ -132,28 +132,45 @@ def cpu_sample(threads=None, n_images=1, rank=0):
     return n_images / dt, desc, cores
 
 
+def host_threads():
+    """Physical cores of the box.  torchrun exports OMP_NUM_THREADS=1 to every rank, which would leave the CPU arm on a
+    single thread; the arm runs on rank 0 alone, so it sets torch's intra-op thread count explicitly.  (All logical
+    threads -- 2 per core -- made the CRAFT forward 10x slower on these hosts: 59 s vs 6 s per page.)"""
+    try:
+        import psutil
+        n = psutil.cpu_count(logical=False)
+    except ImportError:
+        n = None
+    n = int(n or max(1, (os.cpu_count() or 2) // 2))
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))        # a container may see fewer CPUs than the box has cores
+    except AttributeError:
+        pass
+    return max(n, 1)
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0                                        # rank 0 alone runs the CPU arm
-    # torch's default intra-op thread count (= physical cores) is the fastest setting on these hosts:
-    # forcing all 128 hardware threads made the CRAFT forward 10x slower (measured 59 s vs 6 s / page).
+    threads = host_threads()
     for _ in range(1 if args.warmup > 0 else 0):        # one warm-up pass pages everything in (each pass is ~6 s)
-        cpu_sample(None, 1)
+        cpu_sample(threads, 1)
     t0 = time.perf_counter()
     desc, used = "", 0
     for _ in range(args.steps):
-        _, desc, used = cpu_sample(None, 1)
+        _, desc, used = cpu_sample(threads, 1)
     dt = time.perf_counter() - t0
     value = args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
-        "config": dict(workload_config(args.gpus), step="1 page per step (bounded sample of the 32-page batch)"),
+        "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port",
-                         "sample": "oracle port (torch-CPU fp32 CRAFT+CRNN, OpenCV getBoxes/warpBox) -- the reference "
-                                   "needs TensorFlow, which is not installable offline; " + desc},
+                         "sample": "each step = 1 page of the workload's batch (bounded sample), rank 0 only; oracle port "
+                                   "(torch-CPU fp32 CRAFT+CRNN, OpenCV getBoxes/warpBox) -- the reference needs TensorFlow, "
+                                   "which is not installable offline; " + desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
@@ -294,7 +311,7 @@ def run_b200(args):
         "words_per_step": stats["words"],
     }
     if world == 1:
-        v, desc, cores = cpu_sample(None, 1)
+        v, desc, cores = cpu_sample(host_threads(), 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "oracle port of the reference path (TensorFlow not installable offline): " + desc}
     print(json.dumps(line))
