@@ -248,6 +248,9 @@ def run_b200(args):
         torch.cuda.synchronize()
         ms = torch.tensor([e0.elapsed_time(e1)], device=device)
         if world > 1:
+            every = [torch.zeros_like(ms) for _ in range(world)]
+            dist.all_gather(every, ms)
+            stats["per_rank_ms"] = [round(float(t.item()) / steps, 3) for t in every]   # names the limiter: rank 0 (decode) or a slow clock
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         barrier()
         return float(ms.item())
@@ -259,7 +262,10 @@ def run_b200(args):
     if rank == 0:
         sampler.start()
     launches0 = det.ctx.launch_count() + rec.ctx.launch_count()
+    D.stats["decode_ms"], D.stats["decodes"] = 0.0, 0
     ms_dev = timed(pages_dev, args.steps)
+    per_rank_dev = stats.get("per_rank_ms")
+    decode_ms = D.stats["decode_ms"] / max(D.stats["decodes"], 1)
     launches = det.ctx.launch_count() + rec.ctx.launch_count() - launches0
     ms_e2e = timed(pages, args.steps)
     clocks = sampler.stop() if rank == 0 else None
@@ -310,6 +316,9 @@ def run_b200(args):
                      "traffic": traffic},
         "words_per_step": stats["words"],
     }
+    if world > 1:
+        line["per_rank_ms_per_step"] = per_rank_dev
+        line["rank0_decode_ms_per_step"] = round(decode_ms, 3)
     if world == 1:
         v, desc, cores = cpu_sample(host_threads(), 1)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

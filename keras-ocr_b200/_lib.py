@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libb2ocr.so")
+LIB_PATH = os.environ.get("B2O_LIB") or os.path.join(_HERE, "libb2ocr.so")      # B2O_LIB: development builds only
 
 CONV_AUTO, CONV_SIMT, CONV_TC_GENERIC = 0, 1, 2
 MAX_CLASSES = 1024            # B2O_MAX_CLASSES in include/b2ocr.h

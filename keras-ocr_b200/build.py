@@ -34,6 +34,23 @@ def _compile(src):
     return src, r.returncode, r.stdout + r.stderr
 
 
+def build_debug():
+    """Development build with the MMA-warp wait counters compiled in (-DB2O_TC_DEBUG; scripts/dev_tc_debug.py reads
+    them): ``libb2ocr_dbg.so`` next to the product library, picked up with B2O_LIB=<path>.  Never loaded by default."""
+    out = os.path.join(HERE, "libb2ocr_dbg.so")
+    objs = []
+    for src in SOURCES:
+        obj = os.path.join(CSRC, src.replace(".cu", ".dbg.o"))
+        r = subprocess.run([NVCC] + FLAGS + ["-DB2O_TC_DEBUG", "-c", os.path.join(CSRC, src), "-o", obj], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}{r.stderr}")
+        objs.append(obj)
+    r = subprocess.run([NVCC, "-shared", "-o", out] + objs + ["-lcudart"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 def build(force=False, verbose=False):
     if force:
         for s in SOURCES:
@@ -56,4 +73,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_debug() if "--debug-tc" in sys.argv else build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -23,6 +23,7 @@
 //   warps 3..18 = epilogue: tcgen05.ld -> scale/shift/ReLU/affine -> fp16|fp32 NHWC stores (possibly
 //   into a channel slice of a concat buffer) and, optionally, the fused 2x2 max-pool output.
 // * persistent: grid = min(#tiles, #SMs); n-tiles of one pixel tile run back to back.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -71,6 +72,7 @@ struct TcParams {
   __half* pool_out;                       // fused 2x2/2 max-pool output (or null)
   int pool_ld, PH, PW;
   int box16;                              // MODE 3 with ONE 16 x 18 A box per K chunk (dx taps through the descriptor)
+  int debug_nostore;                      // development builds (-DB2O_TC_DEBUG, B2O_DEBUG_NOSTORE=1): epilogue computes but does not store
   // fused CRAFT tail (16-channel layers only): conv_cls.6 (1x1 16->16 ReLU) + conv_cls.8 (1x1 16->2) applied to the
   // epilogue's 16 channels in registers, fp32 (text, link) scores out -- detection.py:404-410
   const float *tail_w6, *tail_b6, *tail_w8, *tail_b8;   // [16][16], [16], [16][2], [2]
@@ -749,7 +751,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
             __half2 hv = __floats2half2_rn(y[j], y[j + 1]);
             pk[j / 2] = *reinterpret_cast<uint32_t*>(&hv);
           }
+#ifdef B2O_TC_DEBUG
+          if (valid && p.write_full && !(p.debug_nostore && pk[0] != 0x12345678u)) {
+#else
           if (valid && p.write_full) {
+#endif
             __half* o = reinterpret_cast<__half*>(p.out) + pix * p.out_ld + c0;
             if (p.wide) {
               st_global_256(o, pk);
@@ -1026,7 +1032,11 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
                 res_bytes * (pair ? 2 : 1) <= (1 << 20) - 1) ? 1 : 0;
   // single-box tiles (default; B2O_TC_BOX16=0 restores three 8-pixel-wide boxes per K chunk): one 16-pixel-wide box per
   // K chunk, where the layer then still runs as whole tiles per barrier (MODE 3).  Same MMA order, bit-identical results.
-  if (ctx->tc_box16 && p.resident && bn <= 128 && ctx->conv_engine == B2O_CONV_AUTO) {
+  // Measured per layer on B200 (profiles/r2b_layers.csv vs r2a): N <= 64 tiles with 64- / 32-channel chunks gain
+  // (conv2 64->64 4.66 -> 4.31 ms, upconv4.3 1.12 -> 0.86, conv_cls.0/.2 0.64 -> 0.57), N = 128 tiles lose 3-5 % (fewer,
+  // larger ring slots) and the 16-channel stem loses 14 % (32-byte pixel rows: the dx-shifted operand reads straddle
+  // the 256-byte swizzle atoms) -- so only the former use it.
+  if (ctx->tc_box16 && p.resident && bn <= 64 && kch >= 32 && ctx->conv_engine == B2O_CONV_AUTO) {
     const int a16 = 18 * 16 * kch * 2;                     // 36864 / 18432 / 9216 B: whole 1 KB units for every swizzle mode
     if ((budget - res_bytes) / a16 >= 2 * kchunks) { p.box16 = 1; p.a_bytes = a16; p.a_stride = a16; }
   }
@@ -1065,6 +1075,9 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   int smem_bytes = p.off_bar + 512 + aff_bytes + 1024;
   if (smem_bytes < 120 * 1024) smem_bytes = 120 * 1024;    // one CTA per SM (TMEM base 0, see kernel)
 
+#ifdef B2O_TC_DEBUG
+  if (const char* e = getenv("B2O_DEBUG_NOSTORE")) p.debug_nostore = atoi(e);
+#endif
   p.s1 = L.s1; p.t1 = L.t1; p.s2 = L.s2; p.t2 = L.t2; p.relu = L.relu;
   if (tail) { p.tail_w6 = tail->w6; p.tail_b6 = tail->b6; p.tail_w8 = tail->w8; p.tail_b8 = tail->b8; p.tail_out = tail->scores; }
   p.out = out.ptr; p.out_ld = out.ld; p.out_f32 = out_f32; p.write_full = write_full;

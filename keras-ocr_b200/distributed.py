@@ -177,9 +177,23 @@ def agree_max_boxes(counts, device=None, floor=16):
     return size
 
 
+stats = {"decode_ms": 0.0, "decodes": 0}      # rank 0's serial host work (bench.py reports it per step)
+
+
 def _decode_blocks(blocks, max_boxes, alphabet):
+    import time
+
     from . import recognition
 
+    t0 = time.perf_counter()
+    try:
+        return _decode_blocks_impl(blocks, max_boxes, alphabet, recognition)
+    finally:
+        stats["decode_ms"] += (time.perf_counter() - t0) * 1e3
+        stats["decodes"] += 1
+
+
+def _decode_blocks_impl(blocks, max_boxes, alphabet, recognition):
     counts, boxes, labels = unpack_blocks(blocks, max_boxes)
     texts = recognition.labels_to_text(labels, alphabet)
     quads, out, start = list(boxes), [], 0             # one (4,2) view per word, made once
