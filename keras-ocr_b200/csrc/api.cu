@@ -342,7 +342,12 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
   const Spec convs[] = {{"conv_1", 1, 64, 3, nullptr},    {"conv_2", 64, 128, 3, nullptr}, {"conv_3", 128, 256, 3, "bn_3"},
                         {"conv_4", 256, 256, 3, nullptr}, {"conv_5", 256, 512, 3, "bn_5"}, {"conv_6", 512, 512, 3, nullptr},
                         {"conv_7", 512, 512, 3, "bn_7"},  {"stn.conv_a", 512, 16, 5, nullptr}, {"stn.conv_b", 16, 32, 5, nullptr}};
+  // build_model(stn=False) (recognition.py:196, 243): a checkpoint without the localisation net's tensors is the
+  // recognizer without the spatial transformer -- the conv features go straight to the reshape + fc_9
+  const bool has_stn = m.count("stn.conv_a.kernel") != 0;
+  ctx->crnn_stn = has_stn;
   for (const Spec& s : convs) {
+    if (!has_stn && std::string(s.name).rfind("stn.", 0) == 0) continue;
     const int64_t wshape[4] = {s.k, s.k, s.cin, s.cout};
     const int64_t vshape[1] = {s.cout};
     const b2o_tensor* w = need(ctx, m, std::string(s.name) + ".kernel", 4, wshape);
@@ -387,6 +392,7 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
   struct Dense { const char* name; int k, n, relu; };
   const Dense dense[] = {{"stn.dense_a", 11200, 64, 1}, {"fc_9", 3584, 128, 1}};
   for (const Dense& d : dense) {
+    if (!has_stn && std::string(d.name).rfind("stn.", 0) == 0) continue;
     const int64_t wshape[2] = {d.k, d.n};
     const int64_t vshape[1] = {d.n};
     const b2o_tensor* w = need(ctx, m, std::string(d.name) + ".kernel", 2, wshape);
@@ -398,7 +404,7 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
     ConvLayer& L = ctx->crnn[d.name];
     B2O_RETURN_IF(build_layer(ctx, L, d.name, d.k, d.n, 1, 1, d.relu, wget, ones(d.n), tovec(b, d.n), nullptr, nullptr, false));
   }
-  {
+  if (has_stn) {
     const int64_t wshape[2] = {64, 6};
     const int64_t vshape[1] = {6};
     const b2o_tensor* w = need(ctx, m, "stn.dense_b.kernel", 2, wshape);
@@ -568,6 +574,10 @@ extern "C" int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in, int b, int32_
   B2O_RETURN_IF(conv_run(ctx, L("conv_5"), x4, x5, 0, st, &p5, 0));
   B2O_RETURN_IF(conv_run(ctx, L("conv_6"), p5, x6, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("conv_7"), x6, x7, 0, st));
+  __half* warped = reinterpret_cast<__half*>(base + p.off_warp);
+  if (!ctx->crnn_stn) {
+    warped = x7.ptr;                                      // stn=False: Reshape consumes bn_7's output directly (282)
+  } else {
   // spatial transformer (263-281)
   if (ctx->conv_engine == B2O_CONV_AUTO && L("stn.conv_a_gemm").block_n != 0) {
     const TensorView y = V(p.off_warp, b, 50, 7, 512);   // the warp buffer is free until stn_sample
@@ -581,8 +591,8 @@ extern "C" int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in, int b, int32_
   B2O_RETURN_IF(conv_run(ctx, L("stn.dense_a"), sb_flat, d1, 0, st));
   float* theta = reinterpret_cast<float*>(base + p.off_theta);
   B2O_RETURN_IF(stn_theta_run(ctx, d1.ptr, b, theta, st));
-  __half* warped = reinterpret_cast<__half*>(base + p.off_warp);
   B2O_RETURN_IF(stn_sample_run(ctx, x7.ptr, theta, b, warped, st));
+  }
   // reshape + fc_9 (282-290)
   const TensorView seq_in = make_view(warped, 1, 1, b * 50, 3584), fc9 = make_view(base + p.off_fc9, 1, 1, b * 50, 128);
   B2O_RETURN_IF(conv_run(ctx, L("fc_9"), seq_in, fc9, 0, st));
@@ -622,6 +632,7 @@ extern "C" int b2o_crnn_tap(b2o_ctx* ctx, const char* name, const void* ws, int 
   size_t off = 0, bytes = 0;
   const std::string s(name);
   if (s == "features") { off = p.off_x7; bytes = B * 50 * 7 * 512 * 2; }
+  else if ((s == "theta" || s == "warped") && !ctx->crnn_stn) { ctx->set_error("b2o_crnn_tap: this recognizer has no spatial transformer"); return B2O_ERR_STATE; }
   else if (s == "theta") { off = p.off_theta; bytes = B * 6 * 4; }
   else if (s == "warped") { off = p.off_warp; bytes = B * 50 * 7 * 512 * 2; }
   else if (s == "fc_9") { off = p.off_fc9; bytes = B * 50 * 128 * 2; }

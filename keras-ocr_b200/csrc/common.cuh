@@ -96,6 +96,7 @@ struct b2o_ctx {
   std::string error;
   std::map<std::string, ConvLayer> craft, crnn;
   bool craft_loaded = false, crnn_loaded = false;
+  bool crnn_stn = true;            // the loaded CRNN has a spatial transformer (build_model(stn=True), the default)
   bool quads_configured = false;   // quads_kernel's dynamic shared-memory opt-in done on this device
   // CRNN tail parameters (device)
   float *stn_d2_w = nullptr, *stn_d2_b = nullptr;              // dense 64 -> 6, fp32

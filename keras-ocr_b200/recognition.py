@@ -9,6 +9,8 @@ from . import _lib, tools, weights as weights_mod
 
 DEFAULT_ALPHABET = string.digits + string.ascii_lowercase      # reference recognition.py:25
 TARGET_HEIGHT, TARGET_WIDTH, STEPS = 31, 200, 48                # DEFAULT_BUILD_PARAMS, recognition.py:13-23
+DEFAULT_BUILD_PARAMS = {"height": 31, "width": 200, "color": False, "filters": (64, 128, 256, 256, 512, 512, 512),
+                        "rnn_units": (128, 128), "dropout": 0.25, "rnn_steps_to_discard": 2, "pool_size": 2}
 
 
 def labels_to_text(rows, alphabet=DEFAULT_ALPHABET):
@@ -43,13 +45,19 @@ class Recognizer:
         weights: ``None`` builds an untrained model for ``alphabet`` (as the reference does); ``"kurapan"`` looks for ``crnn_kurapan.npz`` (exported) or the reference's ``crnn_kurapan.h5``
             (read with h5py where installed) in the cache dir; otherwise a ``.npz`` / ``.h5`` path or a dict
             keyed like ``weights.py``.
-        build_params: must be ``None`` / the defaults (reference recognition.py:13-23).
+        build_params: ``None`` / the defaults (reference recognition.py:13-23), optionally with ``"stn": False`` (the
+            recognizer without the spatial transformer, recognition.py:243); other architectures raise NotImplementedError.
     """
 
     def __init__(self, alphabet=None, weights="kurapan", build_params=None, device=None):
         assert alphabet or weights, "At least one of alphabet or weights must be provided."
-        if build_params is not None:
-            raise NotImplementedError("only DEFAULT_BUILD_PARAMS are supported by the CUDA recognizer")
+        # build_params (recognition.py:13-23, 365-368): the CUDA recognizer implements the default architecture; of the
+        # build options only ``stn`` (with / without the spatial transformer, recognition.py:243) may differ
+        params = dict(DEFAULT_BUILD_PARAMS, **(build_params or {}))
+        self.stn = bool(params.pop("stn", True))
+        if params != DEFAULT_BUILD_PARAMS:
+            changed = sorted(k for k in params if params[k] != DEFAULT_BUILD_PARAMS.get(k))
+            raise NotImplementedError(f"build_params other than the defaults are not supported by the CUDA recognizer: {changed}")
         if not torch.cuda.is_available():
             raise _lib.B2OError("keras-ocr_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
         self.alphabet = alphabet or DEFAULT_ALPHABET              # recognition.py:369-375
@@ -62,7 +70,7 @@ class Recognizer:
             tensors = weights
         elif weights is None:
             # reference recognition.py:382-383: no weights -> the freshly built (untrained) model for this alphabet
-            tensors = weights_mod.synthetic_crnn_weights(seed=0, alphabet=self.alphabet)
+            tensors = weights_mod.synthetic_crnn_weights(seed=0, alphabet=self.alphabet, stn=self.stn)
         elif isinstance(weights, str) and weights.endswith(".npz"):
             tensors = weights_mod.load_npz(weights)
         elif isinstance(weights, str) and weights.endswith(".h5"):
@@ -77,6 +85,11 @@ class Recognizer:
                     "crnn_kurapan.h5", sha256="a7d8086ac8f5c3d6a0a828f7d6fbabcaf815415dd125c32533013f85603be46d"))
         else:
             raise NotImplementedError(f"Cannot load weights from {weights}")
+        has_stn = "stn.conv_a.kernel" in tensors
+        if has_stn and not self.stn:                              # stn=False with a checkpoint that has one: drop it
+            tensors = {k: v for k, v in tensors.items() if not k.startswith("stn.")}
+        elif self.stn and not has_stn:
+            raise ValueError("the checkpoint has no spatial-transformer tensors: pass build_params={'stn': False}")
         n_classes = len(self.alphabet) + 1
         top = tensors.get("fc_12.kernel")
         if top is None or tuple(np.shape(top)) != (256, n_classes):

@@ -195,3 +195,46 @@ def rectify_boxes(boxes, tolerance=1e-3):
         if nearest.max() > tolerance:
             out[k] = rect
     return out
+
+
+# ----------------------------------------------------------------------------------- drawing (host, cv2)
+def drawBoxes(image, boxes, color=(255, 0, 0), thickness=5, boxes_format="boxes"):
+    """tools.drawBoxes (reference tools.py:189-229): polylines of ``boxes`` on a copy of ``image``; ``boxes_format`` is
+    "boxes" ((N,4,2) array as from ``Detector.detect``), "lines" (lists of (box, character)) or "predictions"
+    ((word, box) tuples as from ``Pipeline.recognize``)."""
+    import cv2
+
+    if len(boxes) == 0:
+        return image
+    canvas = image.copy()
+    if boxes_format == "lines":
+        boxes = [box for line in boxes for box, _ in line]
+    if boxes_format == "predictions":
+        boxes = [box for _, box in boxes]
+    for box in boxes:
+        cv2.polylines(img=canvas, pts=box[np.newaxis].astype("int32"), color=color, thickness=thickness, isClosed=True)
+    return canvas
+
+
+def drawAnnotations(image, predictions, ax=None):
+    """tools.drawAnnotations (reference tools.py:150-186): boxes plus the recognised words as margin annotations on a
+    matplotlib axis.  matplotlib is an optional dependency here as it is upstream."""
+    import matplotlib.pyplot as plt
+
+    if ax is None:
+        _, ax = plt.subplots()
+    ax.imshow(drawBoxes(image=image, boxes=predictions, boxes_format="predictions"))
+    predictions = sorted(predictions, key=lambda p: p[1][:, 1].min())
+    left = [(w, b) for w, b in predictions if b[:, 0].min() < image.shape[1] / 2]
+    right = [(w, b) for w, b in predictions if not b[:, 0].min() < image.shape[1] / 2]
+    ax.set_yticks([])
+    ax.set_xticks([])
+    for side, group in zip(["left", "right"], [left, right]):
+        for index, (text, box) in enumerate(group):
+            y = 1 - (index / len(group))
+            xy = box[0] / np.array([image.shape[1], image.shape[0]])
+            xy[1] = 1 - xy[1]
+            ax.annotate(text=text, xy=xy, xytext=(-0.05 if side == "left" else 1.05, y), xycoords="axes fraction",
+                        arrowprops={"arrowstyle": "->", "color": "r"}, color="r", fontsize=14,
+                        horizontalalignment="right" if side == "left" else "left")
+    return ax

@@ -147,9 +147,10 @@ HERSHEY_HEAD = "crnn_hershey_head.npz"      # keras-ocr_b200/data/: fc_9 + BiLST
 HERSHEY_SEED = 2                            # the backbone seed that head was fitted on
 
 
-def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False):
+def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False, stn=True):
     """Seeded CRNN weights keyed by Keras layer name (Keras layouts); the top layer has len(alphabet)+1 classes.
 
+    ``stn=False``: no spatial-transformer tensors (the ``build_model(stn=False)`` variant, recognition.py:196, 243).
     ``decisive=True`` (seed 2, default alphabet only): the convolutional backbone and the spatial transformer keep their
     seeded random weights, and everything after the transformer -- ``fc_9``, the four LSTMs, ``fc_12`` -- comes from
     ``data/crnn_hershey_head.npz``, fitted with CTC loss on the crops the oracle pipeline cuts out of
@@ -195,6 +196,8 @@ def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False):
         w[name + ".bias"] = b
     w["fc_12.kernel"] = _he(rng, (256, len(alphabet) + 1), 256, 8.0)
     w["fc_12.bias"] = (rng.standard_normal(len(alphabet) + 1) * 0.1).astype(np.float32)
+    if not stn:                                     # build_model(stn=False): the same model without the localisation net
+        w = {k: v for k, v in w.items() if not k.startswith("stn.")}
     return w
 
 

@@ -128,8 +128,11 @@ def crnn_logits(weights, crops, return_intermediates=False):
     """Returns the softmax outputs after discarding 2 steps: (B,48,37) float32."""
     w = _t(weights)
     feat = crnn_features(weights, crops)                 # (B,512,50,7)
-    theta = stn_theta(w, feat)
-    warped = stn_sample(feat.permute(0, 2, 3, 1).contiguous(), theta)   # (B,50,7,512)
+    if "stn.conv_a.kernel" in w:
+        theta = stn_theta(w, feat)
+        warped = stn_sample(feat.permute(0, 2, 3, 1).contiguous(), theta)   # (B,50,7,512)
+    else:                                                # build_model(stn=False), recognition.py:243: no transformer
+        theta, warped = None, feat.permute(0, 2, 3, 1).contiguous()
     B = warped.shape[0]
     seq = warped.reshape(B, warped.shape[1], -1)         # Reshape -> (B,50,3584), feature = h*512+c
     seq = F.relu(seq @ w["fc_9.kernel"] + w["fc_9.bias"])

@@ -54,7 +54,7 @@ def reference_tools():
     # annotations in adjust_boxes reference tx.Literal[...]; strip annotations instead of stubbing
     with open(os.path.join(REF, "keras_ocr", "tools.py")) as f:
         tree = ast.parse(f.read())
-    names = {"get_rotated_width_height", "warpBox", "get_rotated_box", "pad", "resize_image", "adjust_boxes", "fix_line", "fit"}
+    names = {"get_rotated_width_height", "warpBox", "get_rotated_box", "pad", "resize_image", "adjust_boxes", "fix_line", "fit", "drawBoxes"}
     body = []
     for node in tree.body:
         if isinstance(node, ast.FunctionDef) and node.name in names:
@@ -206,6 +206,12 @@ def check_inputs(tools, out):
     print("  fit (letterbox / crop): identical")
     boxes = rng.uniform(0, 100, (5, 4, 2)).astype(np.float32)
     assert np.array_equal(tools.adjust_boxes(boxes=boxes, boxes_format="boxes", scale=0.5), boxes * 0.5)
+    canvas = rng.integers(0, 256, (120, 120, 3), dtype=np.uint8)
+    assert np.array_equal(tools.drawBoxes(image=canvas, boxes=boxes), p_tools.drawBoxes(canvas, boxes))
+    preds = [("w", b) for b in boxes]
+    assert np.array_equal(tools.drawBoxes(image=canvas, boxes=preds, boxes_format="predictions", thickness=2),
+                          p_tools.drawBoxes(canvas, preds, thickness=2, boxes_format="predictions"))
+    print("  drawBoxes: identical")
 
 
 def check_craft_keras(out):

@@ -347,6 +347,38 @@ def test_alphabet_mismatch_uses_backbone_only(cuda_device, capsys):
     assert len(out) == 2 and all(set(tx) <= set("xyz") for tx in out)
 
 
+def test_recognizer_without_spatial_transformer(cuda_device):
+    """build_model(stn=False) (recognition.py:196, 243): ``build_params={"stn": False}`` runs the conv stack straight into
+    Reshape + fc_9.  Logits against the fp32 oracle (which takes the same branch), labels = exact collapse of the device's
+    own logits; a checkpoint that HAS a transformer can be loaded with it switched off; other build_params are refused."""
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import crnn, synth
+    w = W.synthetic_crnn_weights(5, stn=False)
+    assert not any(k.startswith("stn.") for k in w)
+    rec = Recognizer(weights=w, build_params={"stn": False})
+    rec.keep_workspace = True
+    rng = np.random.default_rng(4)
+    crops = np.stack([synth.noise_gray(rng, 31, 200) for _ in range(5)])
+    texts = rec.recognize_crops(crops)
+    logits = rec.tap("logits", (5, 48, 37), torch.float32).cpu()
+    with torch.no_grad():
+        probs, inter = crnn.crnn_logits(w, crops.astype(np.float32) / 255, return_intermediates=True)
+    assert inter["theta"] is None
+    assert float((logits - inter["logits"]).abs().max()) <= 0.15
+    fc9 = rec.tap("fc_9", (5, 50, 128), torch.float16).float().cpu()
+    assert float((fc9 - inter["fc_9"]).abs().max() / inter["fc_9"].abs().max()) <= 5e-2
+    assert texts == crnn.labels_to_text(crnn.ctc_greedy(torch.softmax(logits, -1)))
+    with pytest.raises(_lib.B2OError):
+        rec.tap("theta", (5, 6), torch.float32)
+    full = W.synthetic_crnn_weights(5)                               # same seed: identical tensors plus the transformer's
+    again = Recognizer(weights=full, build_params={"stn": False})
+    assert again.recognize_crops(crops) == texts
+    with pytest.raises(ValueError):
+        Recognizer(weights=w)                                        # stn=True (default) needs the transformer's tensors
+    with pytest.raises(NotImplementedError):
+        Recognizer(weights=full, build_params={"color": True})
+
+
 # ------------------------------------------------------------------------------- API behaviour
 def test_reference_api_contract(detector, recognizer):
     rng = np.random.default_rng(0)
