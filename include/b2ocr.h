@@ -123,11 +123,20 @@ int b2o_warp_boxes(b2o_ctx* ctx, const uint8_t* gray_dev, int n, int h, int w,
                    const float* boxes_dev, const int32_t* image_index_dev, int n_boxes,
                    uint8_t* crops_dev, void* crnn_in_dev, void* stream);
 
+/* The same for a recognizer built with color=True (recognition.py:214, 508-510: crops are cut from the RGB image, no
+ * gray conversion): rgb (n,h,w,3) uint8, crops (n_boxes,31,200,3) uint8, crnn_in (n_boxes,200,31,3) fp16.            */
+int b2o_warp_boxes_color(b2o_ctx* ctx, const uint8_t* rgb_dev, int n, int h, int w,
+                         const float* boxes_dev, const int32_t* image_index_dev, int n_boxes,
+                         uint8_t* crops_dev, void* crnn_in_dev, void* stream);
+
 /* prediction_model.predict (recognition.py:535; graph 214-333): CRNN + STN + BiLSTM + greedy CTC.
  * crnn_in: (b,200,31) fp16 from b2o_warp_boxes (or b2o_crops_to_input).  labels: (b,48) int32,
  * merged + blank-free, padded with -1 -- the tensor recognize_from_boxes iterates (527-534).  */
 size_t b2o_crnn_workspace_bytes(int b);
 int b2o_crops_to_input(b2o_ctx* ctx, const uint8_t* crops_dev, int b, void* crnn_in_dev, void* stream);
+/* crops (b,31,200,3) uint8 -> (b,200,31,3) fp16 for a color=True recognizer (conv_1.kernel of shape (3,3,3,64));
+ * b2o_crnn_forward then takes that 3-channel input.                                                              */
+int b2o_crops_to_input_color(b2o_ctx* ctx, const uint8_t* crops_dev, int b, void* crnn_in_dev, void* stream);
 int b2o_crnn_forward(b2o_ctx* ctx, const void* crnn_in_dev, int b, int32_t* labels_dev,
                      void* ws_dev, size_t ws_bytes, void* stream);
 

@@ -51,6 +51,8 @@ SIGNATURES = {
     "b2o_record_floats": (_sz, [_i]),
     "b2o_pack_records": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp]),
     "b2o_warp_boxes": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "b2o_warp_boxes_color": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp]),
+    "b2o_crops_to_input_color": (_i, [_vp, _vp, _i, _vp, _vp]),
     "b2o_crnn_workspace_bytes": (_sz, [_i]),
     "b2o_crops_to_input": (_i, [_vp, _vp, _i, _vp, _vp]),
     "b2o_crnn_forward": (_i, [_vp, _vp, _i, _vp, _vp, _sz, _vp]),
@@ -185,15 +187,16 @@ class Context:
         self._check(self.lib.b2o_pack_records(self.handle, boxes, counts, labels, inv_scale, n, max_boxes, rows,
                                               rec_boxes, records, stream), "b2o_pack_records")
 
-    def warp_boxes(self, gray, n, h, w, boxes, image_index, n_boxes, crops, crnn_in, stream):
-        self._check(self.lib.b2o_warp_boxes(self.handle, gray, n, h, w, boxes, image_index, n_boxes, crops, crnn_in,
-                                            stream), "b2o_warp_boxes")
+    def warp_boxes(self, gray, n, h, w, boxes, image_index, n_boxes, crops, crnn_in, stream, color=False):
+        fn = self.lib.b2o_warp_boxes_color if color else self.lib.b2o_warp_boxes
+        self._check(fn(self.handle, gray, n, h, w, boxes, image_index, n_boxes, crops, crnn_in, stream), "b2o_warp_boxes")
 
     def crnn_workspace_bytes(self, b):
         return int(self.lib.b2o_crnn_workspace_bytes(b))
 
-    def crops_to_input(self, crops, b, crnn_in, stream):
-        self._check(self.lib.b2o_crops_to_input(self.handle, crops, b, crnn_in, stream), "b2o_crops_to_input")
+    def crops_to_input(self, crops, b, crnn_in, stream, color=False):
+        fn = self.lib.b2o_crops_to_input_color if color else self.lib.b2o_crops_to_input
+        self._check(fn(self.handle, crops, b, crnn_in, stream), "b2o_crops_to_input")
 
     def crnn_forward(self, crnn_in, b, labels, ws, ws_bytes, stream):
         self._check(self.lib.b2o_crnn_forward(self.handle, crnn_in, b, labels, ws, ws_bytes, stream), "b2o_crnn_forward")

@@ -113,7 +113,7 @@ struct CraftPlan {
   int n, h1, w1, h2, w2, h4, w4, h8, w8, h16, w16;
   size_t off_a, off_b, off_p1, off_c, off_cat4, off_p2, off_d, off_cat3, off_e, off_p3, off_f, off_cat2, off_g, off_p4,
       off_hh, off_cat1, off_mp, off_s5a, off_u1a, off_u1b, off_u2a, off_u2b, off_u3a, off_u3b, off_u4a, off_u4b, off_h1,
-      off_h2, off_h3, off_x16, bytes;
+      off_h2, off_h3, off_x16, off_z2, off_z3, off_z4, bytes;
 };
 
 // Liveness-based packing: every buffer lives from the launch that first writes it to the launch that last reads it
@@ -165,6 +165,9 @@ CraftPlan plan_craft(int n, int h, int w) {
   take(&p.off_h1, p.h2, p.w2, 32, 27, 28);
   take(&p.off_h2, p.h2, p.w2, 32, 28, 29);
   take(&p.off_h3, p.h2, p.w2, 16, 29, 30);
+  take(&p.off_z2, p.h16, p.w16, 256, 18, 19);      // low-resolution halves of upconv2/3/4.conv.0 (commuted upsampling)
+  take(&p.off_z3, p.h8, p.w8, 128, 21, 22);
+  take(&p.off_z4, p.h4, p.w4, 64, 24, 25);
   std::vector<int> order(bufs.size());
   for (size_t i = 0; i < order.size(); ++i) order[i] = static_cast<int>(i);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return bufs[a].bytes > bufs[b].bytes; });
@@ -238,6 +241,7 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : (atoi(e) == 1 ? 1 : 0);
   if (const char* e = getenv("B2O_TC_BOX16")) ctx->tc_box16 = atoi(e) != 0;
+  if (const char* e = getenv("B2O_UPCONV_COMMUTE")) ctx->no_commute = atoi(e) == 0;      // 1: commuted decoder upsampling (opt-in, see common.cuh)
   if (const char* e = getenv("B2O_FUSED_TAIL")) ctx->no_fused_tail = atoi(e) == 0;      // 0: separate head_tail_kernel (A/B, tests)
   if (const char* e = getenv("B2O_TC_PAIR")) {        // default 1; 0 = single-CTA tiles (A/B runs); 2 = generic tiles too
     ctx->tc_pair = atoi(e) != 0;
@@ -320,6 +324,23 @@ extern "C" int b2o_load_craft(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
     auto wget = [wd, cin, k](int o, int c, int ky, int kx) { return wd[((static_cast<size_t>(o) * cin + c) * k + ky) * k + kx]; };
     ConvLayer& L = ctx->craft[s.name];
     B2O_RETURN_IF(build_layer(ctx, L, s.name, s.cin, s.cout, s.k, s.dil, s.relu, wget, s1, t1, nullptr, nullptr, s.cin == 3));
+    // decoder glue: upconvN.conv.0 reads Concatenate([upsampled decoder (cy channels), encoder tap]); the upsampling
+    // commutes with this 1x1 convolution, so the layer is also kept as two halves -- ".y": the decoder columns, applied
+    // at LOW resolution without bias / BN / ReLU; ".s": the tap columns at full resolution, whose epilogue adds the
+    // upsampled ".y" result before the folded BN + ReLU (detection.py:65-84, 380-390)
+    int cy = 0;
+    if (std::string(s.name) == "upconv2.conv.0") cy = 256;
+    if (std::string(s.name) == "upconv3.conv.0") cy = 128;
+    if (std::string(s.name) == "upconv4.conv.0") cy = 64;
+    if (cy) {
+      auto wy = [wd, cin](int o, int c, int, int) { return wd[static_cast<size_t>(o) * cin + c]; };
+      auto wsk = [wd, cin, cy](int o, int c, int, int) { return wd[static_cast<size_t>(o) * cin + cy + c]; };
+      ConvLayer& Ly = ctx->craft[std::string(s.name) + ".y"];
+      B2O_RETURN_IF(build_layer(ctx, Ly, std::string(s.name) + ".y", cy, s.cout, 1, 1, 0, wy, ones(s.cout),
+                                std::vector<float>(s.cout, 0.0f), nullptr, nullptr, false));
+      ConvLayer& Ls = ctx->craft[std::string(s.name) + ".s"];
+      B2O_RETURN_IF(build_layer(ctx, Ls, std::string(s.name) + ".s", s.cin - cy, s.cout, 1, 1, s.relu, wsk, s1, t1, nullptr, nullptr, false));
+    }
     if (s.cin == 3) {      // tensor-core stem: same filters over a 16-channel (zero-padded) input
       auto wget16 = [wd, cin, k](int o, int c, int ky, int kx) {
         return c < 3 ? wd[((static_cast<size_t>(o) * cin + c) * k + ky) * k + kx] : 0.0f;
@@ -346,7 +367,13 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
   // recognizer without the spatial transformer -- the conv features go straight to the reshape + fc_9
   const bool has_stn = m.count("stn.conv_a.kernel") != 0;
   ctx->crnn_stn = has_stn;
-  for (const Spec& s : convs) {
+  // build_model(color=True) (recognition.py:214): conv_1 takes 3 input channels (RGB crops, no gray conversion)
+  auto c1 = m.find("conv_1.kernel");
+  const int in_ch = (c1 != m.end() && c1->second->ndim == 4 && c1->second->shape[2] == 3) ? 3 : 1;
+  ctx->crnn_in_ch = in_ch;
+  for (const Spec& s0 : convs) {
+    Spec s = s0;
+    if (std::string(s.name) == "conv_1") s.cin = in_ch;
     if (!has_stn && std::string(s.name).rfind("stn.", 0) == 0) continue;
     const int64_t wshape[4] = {s.k, s.k, s.cin, s.cout};
     const int64_t vshape[1] = {s.cout};
@@ -374,7 +401,7 @@ extern "C" int b2o_load_crnn(b2o_ctx* ctx, const b2o_tensor* tensors, int n) {
     };
     ConvLayer& L = ctx->crnn[s.name];
     B2O_RETURN_IF(build_layer(ctx, L, s.name, s.cin, s.cout, s.k, 1, 1, wget, s1, t1, s.bn ? &s2 : nullptr,
-                              s.bn ? &t2 : nullptr, s.cin == 1));
+                              s.bn ? &t2 : nullptr, std::string(s.name) == "conv_1"));
     if (std::string(s.name) == "stn.conv_a") {
       // The 5x5, 512 -> 16 convolution as ONE 1x1 GEMM with N = 25 taps x 16 channels (400, padded to 512)
       // followed by a shift-and-add of the 25 column groups (stn_col2im): 16-column MMAs cost as much tensor
@@ -522,14 +549,28 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
   // decoder (380-390)
   B2O_RETURN_IF(conv_run(ctx, L("upconv1.conv.0"), cat1, u1a, 0, st));
   B2O_RETURN_IF(conv_run(ctx, L("upconv1.conv.3"), u1a, u1b, 0, st));
-  B2O_RETURN_IF(upsample_run(ctx, u1b, cat2_y, st));
-  B2O_RETURN_IF(conv_run(ctx, L("upconv2.conv.0"), cat2, u2a, 0, st));
+  // UpsampleLike + Concatenate + 1x1 conv (380-390).  Opt-in (B2O_UPCONV_COMMUTE=1): where the skip tensor is exactly
+  // twice the decoder tensor the upsampling is commuted behind the convolution -- the decoder half of the 1x1 conv runs
+  // at LOW resolution and the full-resolution half adds its bilinear upsampling in the epilogue, so no upsampled tensor
+  // is written or read back.  Correct (tests) but slower than the explicit UpsampleLike on B200, hence not the default.
+  auto level = [&](const char* name, const TensorView& y, const TensorView& cat_y, const TensorView& cat, const TensorView& skip,
+                   size_t off_z, const TensorView& out) -> int {
+    const std::string base(name);
+    const bool commute = ctx->conv_engine == B2O_CONV_AUTO && !ctx->no_commute && skip.h == 2 * y.h && skip.w == 2 * y.w &&
+                         ctx->craft[base + ".y"].block_n != 0 && ctx->craft[base + ".s"].kch == 64 && ctx->craft[base + ".s"].block_n >= 64;
+    if (!commute) {
+      B2O_RETURN_IF(upsample_run(ctx, y, cat_y, st));
+      return conv_run(ctx, ctx->craft[base], cat, out, 0, st);
+    }
+    const TensorView z = V(off_z, y.h, y.w, out.c);
+    B2O_RETURN_IF(conv_run(ctx, ctx->craft[base + ".y"], y, z, 0, st));
+    return conv_tc_run(ctx, ctx->craft[base + ".s"], skip, out, 0, st, nullptr, 1, nullptr, &z);
+  };
+  B2O_RETURN_IF(level("upconv2.conv.0", u1b, cat2_y, cat2, s3, p.off_z2, u2a));
   B2O_RETURN_IF(conv_run(ctx, L("upconv2.conv.3"), u2a, u2b, 0, st));
-  B2O_RETURN_IF(upsample_run(ctx, u2b, cat3_y, st));
-  B2O_RETURN_IF(conv_run(ctx, L("upconv3.conv.0"), cat3, u3a, 0, st));
+  B2O_RETURN_IF(level("upconv3.conv.0", u2b, cat3_y, cat3, s2, p.off_z3, u3a));
   B2O_RETURN_IF(conv_run(ctx, L("upconv3.conv.3"), u3a, u3b, 0, st));
-  B2O_RETURN_IF(upsample_run(ctx, u3b, cat4_y, st));
-  B2O_RETURN_IF(conv_run(ctx, L("upconv4.conv.0"), cat4, u4a, 0, st));
+  B2O_RETURN_IF(level("upconv4.conv.0", u3b, cat4_y, cat4, s1, p.off_z4, u4a));
   B2O_RETURN_IF(conv_run(ctx, L("upconv4.conv.3"), u4a, u4b, 0, st));
   // head (392-410)
   B2O_RETURN_IF(conv_run(ctx, L("conv_cls.0"), u4b, h1, 0, st));

@@ -90,12 +90,18 @@ struct b2o_ctx {
   bool tc_pair = true;         // CTA pairs (tcgen05 cta_group::2) for the halo-tile layers; B2O_TC_PAIR=0 turns them off
   bool tc_box16 = true;        // one 16 x 18 A box per K chunk in MODE 3 layers (B2O_TC_BOX16=0: three 8 x 18 boxes)
   bool tc_pair_generic = false;   // B2O_TC_PAIR=2: also pair the generic tiles (1x1 / dilated layers): bit-identical, no gain measured (profiles/r2a_ab_pair2.log)
+  // Decoder glue: B2O_UPCONV_COMMUTE=1 commutes the 2x upsampling behind the decoder half of upconvN.conv.0 (low-res GEMM +
+  // upsample-add in the full-resolution layer's epilogue).  Numerically validated, but measured SLOWER on B200
+  // (profiles/r2e_layers.csv: upconv4.0 1.39 + upsample 0.85 ms -> 0.21 + 2.32 ms): the epilogue's per-pixel 16-byte
+  // gathers of the four taps are LSU-wavefront-bound.  Default: explicit UpsampleLike kernels.
+  bool no_commute = true;
   bool no_fused_tail = false;  // B2O_FUSED_TAIL=0: conv_cls.6/.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue
   std::set<const void*> configured;   // kernels whose per-device launch attributes are set on this device
   int64_t launches = 0;
   std::string error;
   std::map<std::string, ConvLayer> craft, crnn;
   bool craft_loaded = false, crnn_loaded = false;
+  int crnn_in_ch = 1;              // 1 = gray crops (default), 3 = RGB crops (build_model(color=True))
   bool crnn_stn = true;            // the loaded CRNN has a spatial transformer (build_model(stn=True), the default)
   bool quads_configured = false;   // quads_kernel's dynamic shared-memory opt-in done on this device
   // CRNN tail parameters (device)
@@ -124,7 +130,10 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L);   // builds wmap / picks block_
 // pool_out != null: also write the 2x2/2 max-pooled output (fused epilogue); write_full = 0 skips `out`
 int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
                 int out_f32, cudaStream_t st, const TensorView* pool_out = nullptr, int write_full = 1,
-                const ConvTail* tail = nullptr);
+                const ConvTail* tail = nullptr, const TensorView* up_add = nullptr);
+// up_add (1x1 layers, 64-channel chunks): a (n, h/2, w/2, cout) fp16 tensor whose exact-2x bilinear upsampling is added to
+// the accumulator before the affine/ReLU -- the decoder's UpsampleLike + Concatenate + 1x1 conv with the upsampling
+// commuted behind the (linear) convolution of the low-resolution half (detection.py:290-309, 380-390)
 int conv_simt_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,
                   int out_f32, cudaStream_t st);
 int conv_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out,

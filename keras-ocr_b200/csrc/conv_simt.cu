@@ -173,13 +173,16 @@ __global__ void normalize16_kernel(const uint8_t* __restrict__ img, long long to
   o[1] = hi;
 }
 
-// CRNN conv_1: x (B,200,31) fp16 -> (B,200,31,64) fp16, 3x3 same, bias + ReLU.
+// CRNN conv_1: x (B,200,31[,CIN]) fp16 -> (B,200,31,64) fp16, 3x3 same, bias + ReLU.  CIN = 1 (gray, the default) or 3
+// (build_model(color=True), recognition.py:214).  Weights [tap][cin][64].
+template <int CIN>
 __global__ void __launch_bounds__(128)
-stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt /*[9][64]*/,
+stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt /*[9*CIN][64]*/,
                  const float* __restrict__ t1, __half* __restrict__ out, int out_ld) {
-  __shared__ float sw[9 * 64];
+  constexpr int K = 9 * CIN;
+  __shared__ float sw[K * 64];
   __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 9 * 64; i += blockDim.x) sw[i] = wgt[i];
+  for (int i = threadIdx.x; i < K * 64; i += blockDim.x) sw[i] = wgt[i];
   if (threadIdx.x < 64) sb[threadIdx.x] = t1[threadIdx.x];
   __syncthreads();
   const long long total = static_cast<long long>(B) * H * W;
@@ -188,14 +191,16 @@ stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float*
   const int w = static_cast<int>(pix % W);
   const int h = static_cast<int>((pix / W) % H);
   const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  float v[9];
+  float v[K];
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
     for (int kx = 0; kx < 3; ++kx) {
       const int ih = h + ky - 1, iw = w + kx - 1;
       const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
-      v[ky * 3 + kx] = ok ? __half2float(x[(static_cast<size_t>(n) * H + ih) * W + iw]) : 0.0f;
+#pragma unroll
+      for (int c = 0; c < CIN; ++c)
+        v[(ky * 3 + kx) * CIN + c] = ok ? __half2float(x[((static_cast<size_t>(n) * H + ih) * W + iw) * CIN + c]) : 0.0f;
     }
   __half* o = out + static_cast<size_t>(pix) * out_ld;
 #pragma unroll 1
@@ -204,7 +209,7 @@ stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float*
 #pragma unroll
     for (int j = 0; j < 16; ++j) acc[j] = sb[cb + j];
 #pragma unroll
-    for (int k = 0; k < 9; ++k)
+    for (int k = 0; k < K; ++k)
 #pragma unroll
       for (int j = 0; j < 16; ++j) acc[j] = fmaf(v[k], sw[k * 64 + cb + j], acc[j]);
     uint32_t pk[8];
@@ -462,7 +467,8 @@ int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __hal
 
 int stem_crnn_run(b2o_ctx* ctx, const ConvLayer& L, const __half* x, int b, const TensorView& out, cudaStream_t st) {
   const long long total = static_cast<long long>(b) * out.h * out.w;
-  stem_crnn_kernel<<<blocks_for(total, 128), 128, 0, st>>>(x, b, out.h, out.w, L.w_f32, L.t1, out.ptr, out.ld);
+  if (L.cin == 3) stem_crnn_kernel<3><<<blocks_for(total, 128), 128, 0, st>>>(x, b, out.h, out.w, L.w_f32, L.t1, out.ptr, out.ld);
+  else stem_crnn_kernel<1><<<blocks_for(total, 128), 128, 0, st>>>(x, b, out.h, out.w, L.w_f32, L.t1, out.ptr, out.ld);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

@@ -75,6 +75,11 @@ struct TcParams {
   int debug_nostore;                      // development builds (-DB2O_TC_DEBUG, B2O_DEBUG_NOSTORE=1): epilogue computes but does not store
   // fused CRAFT tail (16-channel layers only): conv_cls.6 (1x1 16->16 ReLU) + conv_cls.8 (1x1 16->2) applied to the
   // epilogue's 16 channels in registers, fp32 (text, link) scores out -- detection.py:404-410
+  // decoder glue (UPADD instances): the accumulator gets the exact-2x bilinear upsampling (half-pixel centres, clamped
+  // borders -- UpsampleLike, detection.py:290-309) of a low-resolution fp16 tensor (N, H/2, W/2, cout) added BEFORE
+  // the affine/ReLU: relu(bn(W_y.up(y) + W_s.skip)) = relu(bn(up(W_y.y) + W_s.skip)), detection.py:380-390
+  const __half* up_src;
+  int up_ld, UH, UW;
   const float *tail_w6, *tail_b6, *tail_w8, *tail_b8;   // [16][16], [16], [16][2], [2]
   float* tail_out;                        // (N,H,W,2) fp32, or null
 };
@@ -359,7 +364,7 @@ __device__ __forceinline__ void epi_pool8(uint32_t* pk) {
 //       pixel rows (KCH * 2 bytes) inside a swizzle atom, descriptor base offset 0.  2.25x instead of
 //       3.375x of the tile's input crosses L2->SM, in one TMA instruction instead of three and 36 KB instead of 55 KB.
 //       The MMAs are issued in the same (dx, chunk, dy, k) order as without it.
-template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false>
+template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false, bool UPADD = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
                const TcParams p) {
@@ -705,12 +710,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
                                n < p.N;
       const size_t ppix = (static_cast<size_t>(n) * p.PH + (h >> 1)) * p.PW + (w >> 1);
 
+      // UPADD: this pixel's four low-resolution taps (same rule and weights as upsample2x_kernel)
+      size_t up_a = 0, up_b = 0, up_c = 0, up_d = 0;
+      float up_ly = 0.f, up_lx = 0.f;
+      if (UPADD) {
+        const int qy = (h + 1) >> 1, qx = (w + 1) >> 1;
+        const int ya = max(qy - 1, 0), yb = min(qy, p.UH - 1), xa = max(qx - 1, 0), xb = min(qx, p.UW - 1);
+        up_ly = ((h + 1) & 1) ? ((qy == 0) ? 0.0f : 0.75f) : 0.25f;      // ry = (h + 1) & 1
+        up_lx = ((w + 1) & 1) ? ((qx == 0) ? 0.0f : 0.75f) : 0.25f;
+        const size_t nb = static_cast<size_t>(min(n, p.N - 1)) * p.UH;
+        up_a = ((nb + ya) * p.UW + xa) * p.up_ld; up_b = ((nb + ya) * p.UW + xb) * p.up_ld;
+        up_c = ((nb + yb) * p.UW + xa) * p.up_ld; up_d = ((nb + yb) * p.UW + xb) * p.up_ld;
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_after_sync();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quad * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
       // one 16-column chunk: affine/ReLU -> stores (+ fused pool)
-      auto chunk = [&](const uint32_t* v, const int ch) {
+      auto chunk = [&](uint32_t* v, const int ch) {
         const int c0 = c_base + ch * CH;
+        if (UPADD && valid) {
+          // acc += hy * (hx * A + lx * B) + ly * (hx * C + lx * D), the expression of upsample2x_kernel, in fp32
+          const float hy = 1.0f - up_ly, hx = 1.0f - up_lx;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            const uint4 ra = __ldg(reinterpret_cast<const uint4*>(p.up_src + up_a + c0 + 8 * half));
+            const uint4 rb = __ldg(reinterpret_cast<const uint4*>(p.up_src + up_b + c0 + 8 * half));
+            const uint4 rc = __ldg(reinterpret_cast<const uint4*>(p.up_src + up_c + c0 + 8 * half));
+            const uint4 rd = __ldg(reinterpret_cast<const uint4*>(p.up_src + up_d + c0 + 8 * half));
+            const __half2* pa = reinterpret_cast<const __half2*>(&ra);
+            const __half2* pb = reinterpret_cast<const __half2*>(&rb);
+            const __half2* pc = reinterpret_cast<const __half2*>(&rc);
+            const __half2* pd = reinterpret_cast<const __half2*>(&rd);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 fa = __half22float2(pa[i]), fb = __half22float2(pb[i]);
+              const float2 fc = __half22float2(pc[i]), fd = __half22float2(pd[i]);
+              const int j = 8 * half + 2 * i;
+              v[j] = __float_as_uint(__uint_as_float(v[j]) + (hy * (hx * fa.x + up_lx * fb.x) + up_ly * (hx * fc.x + up_lx * fd.x)));
+              v[j + 1] = __float_as_uint(__uint_as_float(v[j + 1]) + (hy * (hx * fa.y + up_lx * fb.y) + up_ly * (hx * fc.y + up_lx * fd.y)));
+            }
+          }
+        }
         float y[CH];
         epi_affine(p, e_s1, e_t1, e_s2, e_t2, v, c0, y);
         if (BLOCK_N == 16 && p.tail_out != nullptr) {        // warp-uniform; only the 16-channel instances carry it
@@ -784,7 +824,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
       constexpr int CH_FIRST_STEP = TILE_PAR ? 1 : 4;
       constexpr int PER_WARP = TILE_PAR ? BLOCK_N / CH : BLOCK_N / CH / 4;
       const int ch_first = TILE_PAR ? 0 : sub;
-      if (PER_WARP >= 2) {
+      if (PER_WARP >= 2 && !UPADD) {
 #pragma unroll 1
         for (int i = 0; i < PER_WARP; i += 2) {
           const int cha = ch_first + i * CH_FIRST_STEP, chb = cha + CH_FIRST_STEP;
@@ -796,10 +836,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
           chunk(vb, chb);
         }
       } else {
-        uint32_t va[CH];
-        tmem_ld<CH>(taddr + static_cast<uint32_t>(ch_first * CH), va);
-        tmem_ld_wait();
-        chunk(va, ch_first);
+        // one chunk at a time (single-chunk tiles, and the UPADD instances, whose tap loads need the registers)
+#pragma unroll 1
+        for (int i = 0; i < PER_WARP; ++i) {
+          const int cha = ch_first + i * CH_FIRST_STEP;
+          uint32_t va[CH];
+          tmem_ld<CH>(taddr + static_cast<uint32_t>(cha * CH), va);
+          tmem_ld_wait();
+          chunk(va, cha);
+        }
       }
       tcgen05_before_sync();
       __syncwarp();
@@ -866,12 +911,12 @@ double pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
 
 constexpr int kRetrySingle = 1;            // launch(): the pair launch was refused, plan the layer again without pairs
 
-template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false>
+template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false, bool UPADD = false>
 int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, int smem_bytes,
            cudaStream_t st) {
-  const void* fn = reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16>);
+  const void* fn = reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD>);
   if (!ctx->configured.count(fn)) {                        // a per-device attribute: remembered per context
-    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16>,
+    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
     ctx->configured.insert(fn);
   }
@@ -896,7 +941,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16>, amap, L.wmap_pair, p);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD>, amap, L.wmap_pair, p);
     if (le != cudaSuccess) {
       // a device / partition that cannot co-schedule two such CTAs on a TPC: fall back, once and for good, to the
       // single-CTA tiles of the same kernel (bit-identical results)
@@ -907,7 +952,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
       return kRetrySingle;
     }
   } else {
-    conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
+    conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
   }
   B2O_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
@@ -965,7 +1010,13 @@ int conv_tc_prepare(b2o_ctx* ctx, ConvLayer& L) {
 }
 
 int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const TensorView& out, int out_f32,
-                cudaStream_t st, const TensorView* pool_out, int write_full, const ConvTail* tail) {
+                cudaStream_t st, const TensorView* pool_out, int write_full, const ConvTail* tail, const TensorView* up_add) {
+  if (up_add != nullptr && (L.ksize != 1 || L.kch != 64 || L.block_n < 64 || out_f32 || pool_out != nullptr || tail != nullptr ||
+                            up_add->c != L.cout || up_add->n != in.n || 2 * up_add->h != in.h || 2 * up_add->w != in.w ||
+                            (up_add->ld % 8) || (reinterpret_cast<uintptr_t>(up_add->ptr) & 15))) {
+    ctx->set_error("conv_tc_run: up_add needs a 1x1 layer with 64-channel chunks and an exactly half-size fp16 tensor (" + L.name + ")");
+    return B2O_ERR_ARG;
+  }
   if (tail != nullptr && (L.block_n != 16 || L.cout != 16 || pool_out != nullptr)) {
     ctx->set_error("conv_tc_run: the fused tail needs a 16-channel layer (" + L.name + ")");
     return B2O_ERR_ARG;
@@ -1006,7 +1057,8 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   // CTA pairs (B2O_TC_PAIR=0 turns them off): halo tiles only; a pair covers two horizontally adjacent tiles, each
   // CTA stages half of the B tile.  The accumulation order per output is the same as without pairs, so the results
   // are bit-identical (tests/test_gpu_parity.py::test_cta_pairs_give_bit_identical_results).
-  const bool pair = ctx->tc_pair && (p.halo || ctx->tc_pair_generic) && L.pair_ok && ctx->conv_engine == B2O_CONV_AUTO;
+  const bool pair = ctx->tc_pair && (p.halo || ctx->tc_pair_generic) && L.pair_ok && ctx->conv_engine == B2O_CONV_AUTO &&
+                    up_add == nullptr;
   if (pair) b_bytes /= 2;
   p.tiles_w = (in.w + (1 << p.bw_log2) - 1) >> p.bw_log2;
   if (pair) p.tiles_w = (p.tiles_w + 1) / 2;                // pair columns
@@ -1079,6 +1131,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   if (const char* e = getenv("B2O_DEBUG_NOSTORE")) p.debug_nostore = atoi(e);
 #endif
   p.s1 = L.s1; p.t1 = L.t1; p.s2 = L.s2; p.t2 = L.t2; p.relu = L.relu;
+  if (up_add) { p.up_src = up_add->ptr; p.up_ld = up_add->ld; p.UH = up_add->h; p.UW = up_add->w; }
   if (tail) { p.tail_w6 = tail->w6; p.tail_b6 = tail->b6; p.tail_w8 = tail->w8; p.tail_b8 = tail->b8; p.tail_out = tail->scores; }
   p.out = out.ptr; p.out_ld = out.ld; p.out_f32 = out_f32; p.write_full = write_full;
   if (want_pool) {
@@ -1110,10 +1163,15 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
                    std::to_string(static_cast<int>(r)));
     return B2O_ERR_CUDA;
   }
+  if (up_add != nullptr) {                                 // generic 1x1 tiles, single CTAs
+    if (bn == 64) return launch<64, 64, 0, false, false, true>(ctx, amap, L, p, smem_bytes, st);
+    if (bn == 128) return launch<128, 64, 0, false, false, true>(ctx, amap, L, p, smem_bytes, st);
+    if (bn == 256) return launch<256, 64, 0, false, false, true>(ctx, amap, L, p, smem_bytes, st);
+  }
 #define B2O_TC_BOX16_PAIR_CASE(BN)                                                                     \
   if (p.box16 && p.group && pair && bn == BN) {                                                       \
     const int rc = launch<BN, 64, 3, true, true>(ctx, amap, L, p, smem_bytes, st);                    \
-    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full, tail) : rc; \
+    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full, tail, up_add) : rc; \
   }
   B2O_TC_BOX16_PAIR_CASE(64); B2O_TC_BOX16_PAIR_CASE(128);
 #undef B2O_TC_BOX16_PAIR_CASE
@@ -1129,7 +1187,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
                    : p.resident            ? launch<BN, 64, 2, true>(ctx, amap, L, p, smem_bytes, st) \
                    : p.halo                ? launch<BN, 64, 1, true>(ctx, amap, L, p, smem_bytes, st) \
                                            : launch<BN, 64, 0, true>(ctx, amap, L, p, smem_bytes, st); \
-    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full, tail) : rc; \
+    return rc == kRetrySingle ? conv_tc_run(ctx, L, in, out, out_f32, st, pool_out, write_full, tail, up_add) : rc; \
   }
   B2O_TC_PAIR_CASE(64); B2O_TC_PAIR_CASE(128); B2O_TC_PAIR_CASE(256);
 #undef B2O_TC_PAIR_CASE

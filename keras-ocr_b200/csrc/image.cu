@@ -176,24 +176,30 @@ __device__ void plan_warp(const float* q /*4x2*/, int target_w, int target_h, Wa
 
 constexpr int kCropH = 31, kCropW = 200;
 
+// CH = 1: gray image (n,H,W), crops (k,31,200), CRNN input (k,200,31).  CH = 3 (build_model(color=True),
+// recognition.py:214, 508-510: no gray conversion): RGB image (n,H,W,3), crops (k,31,200,3), CRNN input (k,200,31,3);
+// cv2.warpPerspective samples every channel with the same coordinates and weights.
+template <int CH>
 __global__ void __launch_bounds__(256)
 warp_kernel(const uint8_t* __restrict__ gray, int n, int H, int W, const float* __restrict__ boxes,
             const int* __restrict__ image_index, uint8_t* __restrict__ crops, __half* __restrict__ crnn_in) {
   __shared__ WarpPlan plan;
-  __shared__ uint8_t tile[kCropH * kCropW];
+  __shared__ uint8_t tile[kCropH * kCropW * CH];
   const int k = blockIdx.x;
   if (threadIdx.x == 0) plan_warp(boxes + static_cast<size_t>(k) * 8, kCropW, kCropH, &plan);
   __syncthreads();
   int img = image_index[k];
   img = min(max(img, 0), n - 1);
-  const uint8_t* g = gray + static_cast<size_t>(img) * H * W;
+  const uint8_t* g = gray + static_cast<size_t>(img) * H * W * CH;
   const int dw = plan.valid ? min(plan.dw, kCropW) : 0, dh = plan.valid ? min(plan.dh, kCropH) : 0;
   // block structure of cv::WarpPerspectiveInvoker (decides where X0/Y0/W0 are re-based)
   int bh0 = min(16, max(dh, 1));
   const int bw0 = min(1024 / bh0, max(dw, 1));
   for (int i = threadIdx.x; i < kCropH * kCropW; i += blockDim.x) {
     const int y = i / kCropW, x = i - y * kCropW;
-    int v = 0;
+    int v[CH];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) v[c] = 0;
     if (x < dw && y < dh) {
       const double* m = plan.m;
       const int bx = (x / bw0) * bw0, x1 = x - bx;
@@ -209,35 +215,45 @@ warp_kernel(const uint8_t* __restrict__ gray, int n, int H, int W, const float* 
       const int ax = X & 31, ay = Y & 31;
       const bool x0ok = sx >= 0 && sx < W, x1ok = sx + 1 >= 0 && sx + 1 < W;
       const bool y0ok = sy >= 0 && sy < H, y1ok = sy + 1 >= 0 && sy + 1 < H;
-      const int p00 = (x0ok && y0ok) ? g[static_cast<size_t>(sy) * W + sx] : 0;
-      const int p01 = (x1ok && y0ok) ? g[static_cast<size_t>(sy) * W + sx + 1] : 0;
-      const int p10 = (x0ok && y1ok) ? g[static_cast<size_t>(sy + 1) * W + sx] : 0;
-      const int p11 = (x1ok && y1ok) ? g[static_cast<size_t>(sy + 1) * W + sx + 1] : 0;
       // BilinearTab_i: (1-fx)(1-fy) ... scaled to 2^15; exact for 1/32 steps
       const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32;
       const int w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
-      v = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 16384) >> 15;
+#pragma unroll
+      for (int c = 0; c < CH; ++c) {
+        const int p00 = (x0ok && y0ok) ? g[(static_cast<size_t>(sy) * W + sx) * CH + c] : 0;
+        const int p01 = (x1ok && y0ok) ? g[(static_cast<size_t>(sy) * W + sx + 1) * CH + c] : 0;
+        const int p10 = (x0ok && y1ok) ? g[(static_cast<size_t>(sy + 1) * W + sx) * CH + c] : 0;
+        const int p11 = (x1ok && y1ok) ? g[(static_cast<size_t>(sy + 1) * W + sx + 1) * CH + c] : 0;
+        v[c] = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 16384) >> 15;
+      }
     }
-    tile[i] = static_cast<uint8_t>(v);
-    if (crops) crops[static_cast<size_t>(k) * kCropH * kCropW + i] = static_cast<uint8_t>(v);
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      tile[i * CH + c] = static_cast<uint8_t>(v[c]);
+      if (crops) crops[(static_cast<size_t>(k) * kCropH * kCropW + i) * CH + c] = static_cast<uint8_t>(v[c]);
+    }
   }
   if (crnn_in == nullptr) return;
   __syncthreads();
   // CRNN input layout (recognition.py:215-216): x[t][j] = crop[30-j][t] / 255
-  __half* o = crnn_in + static_cast<size_t>(k) * kCropH * kCropW;
-  for (int i = threadIdx.x; i < kCropH * kCropW; i += blockDim.x) {
-    const int t = i / kCropH, j = i - t * kCropH;
-    o[i] = __float2half_rn(static_cast<float>(tile[(kCropH - 1 - j) * kCropW + t]) / 255.0f);
+  __half* o = crnn_in + static_cast<size_t>(k) * kCropH * kCropW * CH;
+  for (int i = threadIdx.x; i < kCropH * kCropW * CH; i += blockDim.x) {
+    const int c = i % CH, q = i / CH;
+    const int t = q / kCropH, j = q - t * kCropH;
+    o[i] = __float2half_rn(static_cast<float>(tile[((kCropH - 1 - j) * kCropW + t) * CH + c]) / 255.0f);
   }
 }
 
-__global__ void crops_to_input_kernel(const uint8_t* __restrict__ crops, long long total, __half* __restrict__ out) {
+// crops (k,31,200[,ch]) u8 -> CRNN input (k,200,31[,ch]) fp16 = crop / 255 after Permute((2,1,3)) and the axis flip
+__global__ void crops_to_input_kernel(const uint8_t* __restrict__ crops, long long total, int ch, __half* __restrict__ out) {
   const long long p = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (p >= total) return;
-  const long long k = p / (kCropH * kCropW);
-  const int i = static_cast<int>(p - k * kCropH * kCropW);
-  const int t = i / kCropH, j = i - t * kCropH;
-  out[p] = __float2half_rn(static_cast<float>(crops[k * kCropH * kCropW + (kCropH - 1 - j) * kCropW + t]) / 255.0f);
+  const int per = kCropH * kCropW * ch;
+  const long long k = p / per;
+  const int i = static_cast<int>(p - k * per);
+  const int c = i % ch, q = i / ch;
+  const int t = q / kCropH, j = q - t * kCropH;
+  out[p] = __float2half_rn(static_cast<float>(crops[k * per + ((kCropH - 1 - j) * kCropW + t) * ch + c]) / 255.0f);
 }
 
 }  // namespace
@@ -283,29 +299,48 @@ extern "C" int b2o_rgb_to_gray(b2o_ctx* ctx, const uint8_t* img, int n, int h, i
   return B2O_OK;
 }
 
-extern "C" int b2o_warp_boxes(b2o_ctx* ctx, const uint8_t* gray, int n, int h, int w, const float* boxes,
-                              const int32_t* image_index, int n_boxes, uint8_t* crops, void* crnn_in, void* stream) {
+static int warp_boxes_impl(b2o_ctx* ctx, const uint8_t* img, int ch, int n, int h, int w, const float* boxes,
+                           const int32_t* image_index, int n_boxes, uint8_t* crops, void* crnn_in, void* stream) {
   if (!ctx) return B2O_ERR_ARG;
   DeviceGuard guard(ctx->device);
   if (n_boxes == 0) return B2O_OK;
-  if (!gray || !boxes || !image_index || n <= 0 || h <= 0 || w <= 0 || n_boxes < 0 || (!crops && !crnn_in)) {
+  if (!img || !boxes || !image_index || n <= 0 || h <= 0 || w <= 0 || n_boxes < 0 || (!crops && !crnn_in)) {
     ctx->set_error("b2o_warp_boxes: bad argument");
     return B2O_ERR_ARG;
   }
-  warp_kernel<<<n_boxes, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(gray, n, h, w, boxes, image_index, crops,
-                                                                         reinterpret_cast<__half*>(crnn_in));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (ch == 3) warp_kernel<3><<<n_boxes, 256, 0, st>>>(img, n, h, w, boxes, image_index, crops, reinterpret_cast<__half*>(crnn_in));
+  else warp_kernel<1><<<n_boxes, 256, 0, st>>>(img, n, h, w, boxes, image_index, crops, reinterpret_cast<__half*>(crnn_in));
+  B2O_LAUNCH_CHECK(ctx);
+  return B2O_OK;
+}
+
+extern "C" int b2o_warp_boxes(b2o_ctx* ctx, const uint8_t* gray, int n, int h, int w, const float* boxes,
+                              const int32_t* image_index, int n_boxes, uint8_t* crops, void* crnn_in, void* stream) {
+  return warp_boxes_impl(ctx, gray, 1, n, h, w, boxes, image_index, n_boxes, crops, crnn_in, stream);
+}
+
+extern "C" int b2o_warp_boxes_color(b2o_ctx* ctx, const uint8_t* rgb, int n, int h, int w, const float* boxes,
+                                    const int32_t* image_index, int n_boxes, uint8_t* crops, void* crnn_in, void* stream) {
+  return warp_boxes_impl(ctx, rgb, 3, n, h, w, boxes, image_index, n_boxes, crops, crnn_in, stream);
+}
+
+static int crops_to_input_impl(b2o_ctx* ctx, const uint8_t* crops, int ch, int b, void* crnn_in, void* stream) {
+  if (!ctx) return B2O_ERR_ARG;
+  DeviceGuard guard(ctx->device);
+  if (b == 0) return B2O_OK;
+  if (!crops || !crnn_in || b < 0) { ctx->set_error("b2o_crops_to_input: bad argument"); return B2O_ERR_ARG; }
+  const long long total = static_cast<long long>(b) * kCropH * kCropW * ch;
+  crops_to_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      crops, total, ch, reinterpret_cast<__half*>(crnn_in));
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }
 
 extern "C" int b2o_crops_to_input(b2o_ctx* ctx, const uint8_t* crops, int b, void* crnn_in, void* stream) {
-  if (!ctx) return B2O_ERR_ARG;
-  DeviceGuard guard(ctx->device);
-  if (b == 0) return B2O_OK;
-  if (!crops || !crnn_in || b < 0) { ctx->set_error("b2o_crops_to_input: bad argument"); return B2O_ERR_ARG; }
-  const long long total = static_cast<long long>(b) * kCropH * kCropW;
-  crops_to_input_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      crops, total, reinterpret_cast<__half*>(crnn_in));
-  B2O_LAUNCH_CHECK(ctx);
-  return B2O_OK;
+  return crops_to_input_impl(ctx, crops, 1, b, crnn_in, stream);
+}
+
+extern "C" int b2o_crops_to_input_color(b2o_ctx* ctx, const uint8_t* crops, int b, void* crnn_in, void* stream) {
+  return crops_to_input_impl(ctx, crops, 3, b, crnn_in, stream);
 }

@@ -142,7 +142,10 @@ def minimum_rotated_rectangle(points):
         vx, vy = -uy, ux
         a, b = hull @ np.array([ux, uy]), hull @ np.array([vx, vy])          # coordinates in the edge's frame
         area = (a.max() - a.min()) * (b.max() - b.min())
-        if best_area is None or area < best_area:
+        # Ties are common (two edges whose rectangles are spanned by the same triangle of the quad have equal areas in
+        # exact arithmetic): an edge only wins if it is smaller by more than rounding, i.e. the FIRST edge in hull order
+        # (counter-clockwise from the lexicographically smallest vertex) wins a tie.
+        if best_area is None or area < best_area * (1.0 - 1e-9):
             corners = np.array([[a.min(), b.min()], [a.max(), b.min()], [a.max(), b.max()], [a.min(), b.max()]])
             best = corners @ np.array([[ux, uy], [vx, vy]])                  # back to image coordinates
             best_area = area

@@ -142,7 +142,7 @@ def min_rotated_rectangle(points):
         xs = [ux * x + uy * y for x, y in hull]
         ys = [vx * x + vy * y for x, y in hull]
         area = (max(xs) - min(xs)) * (max(ys) - min(ys))
-        if best is None or area < best[0]:
+        if best is None or area < best[0] * (1.0 - 1e-9):      # exact ties are common for quads: the first edge in hull order wins
             env = [(min(xs), min(ys)), (max(xs), min(ys)), (max(xs), max(ys)), (min(xs), max(ys))]
             best = (area, [(ux * a + vx * b, uy * a + vy * b) for a, b in env])
     return np.array(best[1], dtype=np.float64)

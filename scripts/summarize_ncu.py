@@ -23,6 +23,14 @@ CRAFT = [("stem", 1, 27, 64), ("slice1.3", 1, 576, 64), ("slice1.7", 4, 576, 128
          ("upconv2.0", 64, 768, 256), ("upconv2.3", 64, 2304, 128), ("upconv3.0", 16, 384, 128), ("upconv3.3", 16, 1152, 64),
          ("upconv4.0", 4, 192, 64), ("upconv4.3", 4, 576, 32), ("conv_cls.0", 4, 288, 32), ("conv_cls.2", 4, 288, 32),
          ("conv_cls.4", 4, 288, 16)]
+# with the commuted decoder upsampling (default since r2e) upconv2/3/4.conv.0 run as a low-resolution ".y" GEMM + a ".s" layer
+CRAFT_COMMUTED = []
+for _name, _div, _k, _co in CRAFT:
+    _split = {"upconv2.0": 256, "upconv3.0": 128, "upconv4.0": 64}.get(_name)
+    if _split:
+        CRAFT_COMMUTED += [(_name + ".y", _div * 4, _split, _co), (_name + ".s", _div, _k - _split, _co)]
+    else:
+        CRAFT_COMMUTED.append((_name, _div, _k, _co))
 CRNN = [("conv_2", 6200, 576, 128), ("conv_3", 6200, 1152, 256), ("conv_4", 1500, 2304, 256), ("conv_5", 1500, 2304, 512),
         ("conv_6", 350, 4608, 512), ("conv_7", 350, 4608, 512), ("stn.conv_a", 350, 12800, 16), ("stn.conv_b", 350, 400, 32),
         ("stn.dense_a", 1, 11200, 64), ("fc_9", 50, 3584, 128), ("lstm_in_1", 50, 128, 1024), ("lstm_in_2", 50, 128, 1024)]
@@ -49,13 +57,13 @@ def main():
     order = [launches[k] for k in sorted(launches)]
     conv = [d for d in order if d["kernel"].startswith("conv_tc_kernel")]
     crops = None
-    names = []
+    craft = CRAFT_COMMUTED if len(conv) == len(CRAFT_COMMUTED) + len(CRNN) else CRAFT
     for i, d in enumerate(conv):
-        if i < len(CRAFT):
-            n, div, k, co = CRAFT[i]
+        if i < len(craft):
+            n, div, k, co = craft[i]
             d["layer"], d["flop"] = "craft." + n, 2.0 * pages * px / div * k * co
         else:
-            n, per, k, co = CRNN[i - len(CRAFT)]
+            n, per, k, co = CRNN[i - len(craft)]
             if crops is None:                      # crops = grid-independent: recover from the DRAM-free fact that conv_2 is per crop
                 crops = int(sys.argv[5]) if len(sys.argv) > 5 else 1028
             d["layer"], d["flop"] = "crnn." + n, 2.0 * crops * per * k * co

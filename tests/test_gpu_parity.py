@@ -379,6 +379,36 @@ def test_recognizer_without_spatial_transformer(cuda_device):
         Recognizer(weights=full, build_params={"color": True})
 
 
+def test_recognize_from_boxes_with_caller_supplied_quads(recognizer):
+    """tools.warpBox on quads that are NOT rectangles (reference tools.py:88-95: minimum rotated rectangle first) and on a
+    degenerate box (ZeroDivisionError, tools.py:95): the host rectification of ``recognize_from_boxes`` + the CUDA warp
+    against the oracle's ``warp_box``, which carries its own restatement of the same rule."""
+    from keras_ocr_b200 import tools
+    from oracle import imageops, synth
+    rng = np.random.default_rng(17)
+    gray = synth.noise_gray(rng, 300, 400)
+    rects = synth.random_quads(rng, 24, 300, 400, min_side=20, max_side=160)
+    quads = rects + rng.uniform(-6, 6, rects.shape).astype(np.float32)          # skewed: no longer rectangles
+    fixed = tools.rectify_boxes(quads)
+    assert np.abs(fixed - quads).max() > 1.0                                     # really replaced by their rectangles
+    assert np.array_equal(tools.rectify_boxes(rects), rects)                     # rectangles pass through bit for bit
+    g = torch.from_numpy(gray[None]).to(recognizer.device)
+    idx = torch.zeros(len(fixed), dtype=torch.int32, device=recognizer.device)
+    _, crops = recognizer.warp_device(g, torch.from_numpy(fixed).to(recognizer.device), idx, want_crops=True)
+    crops = crops.cpu().numpy().astype(np.int16)
+    ref = np.stack([imageops.warp_box(gray, q) for q in quads]).astype(np.int16)
+    diff = np.abs(crops - ref)
+    # the two restatements of the rectangle agree to ~1e-5 px; cv2's fixed-point sampler then differs by at most a level
+    assert diff.max() <= 2 and (diff > 0).mean() <= 5e-3, (int(diff.max()), float((diff > 0).mean()))
+    image = np.repeat(gray[..., None], 3, axis=2)
+    texts = recognizer.recognize_from_boxes([image], [quads])
+    assert len(texts) == 1 and len(texts[0]) == len(quads)
+    with pytest.raises(ZeroDivisionError):
+        recognizer.recognize_from_boxes([image], [np.array([[[10, 10], [10.4, 10], [10.4, 60], [10, 60]]], np.float32)])
+    with pytest.raises(ZeroDivisionError):
+        imageops.warp_box(gray, np.array([[10, 10], [10.4, 10], [10.4, 60], [10, 60]], np.float32))
+
+
 # ------------------------------------------------------------------------------- API behaviour
 def test_reference_api_contract(detector, recognizer):
     rng = np.random.default_rng(0)
@@ -706,6 +736,32 @@ def test_cta_pairs_give_bit_identical_results(cuda_device, monkeypatch):
         labels = rec.predict_device(x).clone()
         logits.append((labels, rec.tap("logits", (9, 48, 37), torch.float32).clone()))
     assert torch.equal(logits[0][0], logits[1][0]) and torch.equal(logits[0][1], logits[1][1])
+
+
+def test_decoder_commute_matches_explicit_upsample(cuda_device, monkeypatch, golden_dir):
+    """Decoder glue (detection.py:290-309, 380-390): with B2O_UPCONV_COMMUTE=1 the bilinear 2x upsampling is commuted behind
+    the decoder half of each 1x1 ``upconvN.conv.0`` (low-resolution GEMM + upsample-add in the full-resolution layer's
+    epilogue); the default runs UpsampleLike + the concat-wide convolution as the reference graph does.  The two are the
+    same function up to fp16 rounding of one intermediate: score maps agree to 5e-3 of the range, and BOTH stay within
+    the 2e-2 bound against the reference's own output (golden "even" case, whose sizes are multiples of 16)."""
+    from keras_ocr_b200.detection import Detector
+    cw = W.synthetic_craft_weights(3)
+    monkeypatch.setenv("B2O_UPCONV_COMMUTE", "1")
+    commuted = Detector(weights=cw)
+    monkeypatch.delenv("B2O_UPCONV_COMMUTE")
+    explicit = Detector(weights=cw)
+    rng = np.random.default_rng(7)
+    for h, w in ((160, 224), (768, 768), (144, 200)):          # 144 x 200: 200 / 16 is odd -> one level falls back
+        img = torch.from_numpy(rng.integers(0, 256, (2, h, w, 3), dtype=np.uint8)).to(cuda_device)
+        a, b = commuted.predict_device(img).clone(), explicit.predict_device(img).clone()
+        span = max(float(b.abs().max()), 1.0)
+        assert float((a - b).abs().max()) / span <= 5e-3, (h, w)
+    g = np.load(os.path.join(golden_dir, "craft.npz"))
+    img = torch.from_numpy(g["craft_even_image"]).to(cuda_device)
+    ref = g["craft_even_scores"]
+    for det in (commuted, explicit):
+        err = np.abs(det.predict_device(img).cpu().numpy() - ref).max() / max(np.abs(ref).max(), 1.0)
+        assert err <= 2e-2, err
 
 
 @pytest.mark.parametrize("switch", [("B2O_TC_BOX16", "0"), ("B2O_TC_PAIR", "2"), ("B2O_FUSED_TAIL", "0")],
