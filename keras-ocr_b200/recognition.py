@@ -46,15 +46,19 @@ class Recognizer:
             (read with h5py where installed) in the cache dir; otherwise a ``.npz`` / ``.h5`` path or a dict
             keyed like ``weights.py``.
         build_params: ``None`` / the defaults (reference recognition.py:13-23), optionally with ``"stn": False`` (the
-            recognizer without the spatial transformer, recognition.py:243); other architectures raise NotImplementedError.
+            recognizer without the spatial transformer, recognition.py:243) and / or ``"color": True`` (RGB crops into a
+            3-channel ``conv_1``, recognition.py:214); other architectures raise NotImplementedError.
     """
 
     def __init__(self, alphabet=None, weights="kurapan", build_params=None, device=None):
         assert alphabet or weights, "At least one of alphabet or weights must be provided."
         # build_params (recognition.py:13-23, 365-368): the CUDA recognizer implements the default architecture; of the
-        # build options only ``stn`` (with / without the spatial transformer, recognition.py:243) may differ
+        # build options only ``stn`` (with / without the spatial transformer, recognition.py:243) and ``color`` (RGB instead
+        # of gray crops, recognition.py:214) may differ
         params = dict(DEFAULT_BUILD_PARAMS, **(build_params or {}))
         self.stn = bool(params.pop("stn", True))
+        self.color = bool(params["color"])                        # RGB crops, no gray conversion (recognition.py:214, 508-510)
+        params["color"] = False
         if params != DEFAULT_BUILD_PARAMS:
             changed = sorted(k for k in params if params[k] != DEFAULT_BUILD_PARAMS.get(k))
             raise NotImplementedError(f"build_params other than the defaults are not supported by the CUDA recognizer: {changed}")
@@ -70,7 +74,7 @@ class Recognizer:
             tensors = weights
         elif weights is None:
             # reference recognition.py:382-383: no weights -> the freshly built (untrained) model for this alphabet
-            tensors = weights_mod.synthetic_crnn_weights(seed=0, alphabet=self.alphabet, stn=self.stn)
+            tensors = weights_mod.synthetic_crnn_weights(seed=0, alphabet=self.alphabet, stn=self.stn, color=self.color)
         elif isinstance(weights, str) and weights.endswith(".npz"):
             tensors = weights_mod.load_npz(weights)
         elif isinstance(weights, str) and weights.endswith(".h5"):
@@ -90,6 +94,9 @@ class Recognizer:
             tensors = {k: v for k, v in tensors.items() if not k.startswith("stn.")}
         elif self.stn and not has_stn:
             raise ValueError("the checkpoint has no spatial-transformer tensors: pass build_params={'stn': False}")
+        in_ch = int(np.shape(tensors["conv_1.kernel"])[2]) if "conv_1.kernel" in tensors else 1
+        if in_ch != (3 if self.color else 1):
+            raise ValueError(f"conv_1.kernel takes {in_ch} input channel(s): pass build_params={{'color': {in_ch == 3}}}")
         n_classes = len(self.alphabet) + 1
         top = tensors.get("fc_12.kernel")
         if top is None or tuple(np.shape(top)) != (256, n_classes):
@@ -123,14 +130,18 @@ class Recognizer:
         return gray
 
     def warp_device(self, gray, boxes_flat, image_index, want_crops=False):
-        """tools.warpBox for every box.  Returns (crnn_in (B,200,31) fp16, crops (B,31,200) u8 or None)."""
-        n, h, w = gray.shape
+        """tools.warpBox for every box.  ``gray``: (N,H,W) u8 -- or the RGB batch (N,H,W,3) for a color recognizer.
+        Returns (crnn_in (B,200,31[,3]) fp16, crops (B,31,200[,3]) u8 or None)."""
+        n, h, w = gray.shape[:3]
+        color = gray.dim() == 4
+        assert color == self.color, "a color recognizer warps the RGB batch, a gray one the gray batch"
+        tail = (3,) if color else ()
         b = boxes_flat.shape[0]
-        crnn_in = torch.empty((b, TARGET_WIDTH, TARGET_HEIGHT), dtype=torch.float16, device=self.device)
-        crops = torch.empty((b, TARGET_HEIGHT, TARGET_WIDTH), dtype=torch.uint8, device=self.device) if want_crops else None
+        crnn_in = torch.empty((b, TARGET_WIDTH, TARGET_HEIGHT) + tail, dtype=torch.float16, device=self.device)
+        crops = torch.empty((b, TARGET_HEIGHT, TARGET_WIDTH) + tail, dtype=torch.uint8, device=self.device) if want_crops else None
         self.ctx.warp_boxes(gray.data_ptr(), n, h, w, boxes_flat.data_ptr(), image_index.data_ptr(), b,
                             crops.data_ptr() if want_crops else None, crnn_in.data_ptr(),
-                            torch.cuda.current_stream(self.device).cuda_stream)
+                            torch.cuda.current_stream(self.device).cuda_stream, color=color)
         return crnn_in, crops
 
     def predict_device(self, crnn_in):
@@ -156,14 +167,16 @@ class Recognizer:
         return out
 
     def recognize_crops(self, crops):
-        """crops: (B,31,200) uint8 (ndarray or tensor), i.e. what tools.warpBox returns -> list[str]."""
+        """crops: (B,31,200) uint8 -- (B,31,200,3) for a color recognizer -- i.e. what tools.warpBox returns -> list[str]."""
         t = crops if isinstance(crops, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(crops))
         t = t.to(self.device).contiguous()
         b = t.shape[0]
         if b == 0:
             return []
-        crnn_in = torch.empty((b, TARGET_WIDTH, TARGET_HEIGHT), dtype=torch.float16, device=self.device)
-        self.ctx.crops_to_input(t.data_ptr(), b, crnn_in.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream)
+        assert t.shape[1:] == (TARGET_HEIGHT, TARGET_WIDTH) + ((3,) if self.color else ()), "crops must be (B,31,200[,3])"
+        crnn_in = torch.empty((b, TARGET_WIDTH, TARGET_HEIGHT) + ((3,) if self.color else ()), dtype=torch.float16, device=self.device)
+        self.ctx.crops_to_input(t.data_ptr(), b, crnn_in.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream,
+                                color=self.color)
         return labels_to_text(self.predict_device(crnn_in).cpu().numpy(), self.alphabet)
 
     def recognize(self, image):
@@ -172,9 +185,9 @@ class Recognizer:
         import cv2
 
         image = tools.read_and_fit(filepath_or_array=image, width=TARGET_WIDTH, height=TARGET_HEIGHT, cval=0)
-        if image.ndim == 3 and image.shape[-1] == 3:
+        if not self.color and image.ndim == 3 and image.shape[-1] == 3:      # recognition.py:481-483
             image = cv2.cvtColor(image, code=cv2.COLOR_RGB2GRAY)
-        return self.recognize_crops(np.ascontiguousarray(image.reshape(1, TARGET_HEIGHT, TARGET_WIDTH)))[0]
+        return self.recognize_crops(np.ascontiguousarray(image.reshape((1, TARGET_HEIGHT, TARGET_WIDTH) + ((3,) if self.color else ()))))[0]
 
     def recognize_from_boxes_device(self, images_t, boxes, counts, gray=None, flat=None, image_index=None):
         """images_t (N,H,W,3) u8 CUDA; boxes (N,M,4,2) f32 CUDA; counts host ndarray -> labels (B,48) i32 CUDA.
@@ -187,7 +200,9 @@ class Recognizer:
         total = int(np.minimum(counts, m).sum())
         if total == 0:
             return None
-        if gray is None:
+        if self.color:
+            gray = images_t                                       # color recognizer: crops come straight from the RGB batch
+        elif gray is None:
             gray = self.gray_device(images_t)
         if flat is None or image_index is None:
             n = len(counts)
@@ -216,7 +231,7 @@ class Recognizer:
         flat = tools.rectify_boxes(flat)
         flat_t = torch.from_numpy(np.ascontiguousarray(flat)).to(self.device)
         idx = torch.from_numpy(np.repeat(np.arange(len(counts), dtype=np.int32), counts)).to(self.device)
-        crnn_in, _ = self.warp_device(self.gray_device(images_t), flat_t, idx)
+        crnn_in, _ = self.warp_device(images_t if self.color else self.gray_device(images_t), flat_t, idx)
         predictions = labels_to_text(self.predict_device(crnn_in).cpu().numpy(), self.alphabet)
         ends = np.cumsum(counts)
         return [predictions[int(e - c):int(e)] for c, e in zip(counts, ends)]

@@ -147,9 +147,10 @@ HERSHEY_HEAD = "crnn_hershey_head.npz"      # keras-ocr_b200/data/: fc_9 + BiLST
 HERSHEY_SEED = 2                            # the backbone seed that head was fitted on
 
 
-def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False, stn=True):
+def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False, stn=True, color=False):
     """Seeded CRNN weights keyed by Keras layer name (Keras layouts); the top layer has len(alphabet)+1 classes.
 
+    ``color=True``: ``conv_1`` takes 3 input channels (``build_model(color=True)``, recognition.py:214).
     ``stn=False``: no spatial-transformer tensors (the ``build_model(stn=False)`` variant, recognition.py:196, 243).
     ``decisive=True`` (seed 2, default alphabet only): the convolutional backbone and the spatial transformer keep their
     seeded random weights, and everything after the transformer -- ``fc_9``, the four LSTMs, ``fc_12`` -- comes from
@@ -196,6 +197,8 @@ def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False, stn=True):
         w[name + ".bias"] = b
     w["fc_12.kernel"] = _he(rng, (256, len(alphabet) + 1), 256, 8.0)
     w["fc_12.bias"] = (rng.standard_normal(len(alphabet) + 1) * 0.1).astype(np.float32)
+    if color:                                       # build_model(color=True): conv_1 over RGB crops (own stream: the rest is unchanged)
+        w["conv_1.kernel"] = _he(np.random.default_rng(seed + 7919), (3, 3, 3, 64), 27)
     if not stn:                                     # build_model(stn=False): the same model without the localisation net
         w = {k: v for k, v in w.items() if not k.startswith("stn.")}
     return w

@@ -104,13 +104,14 @@ def lstm(w, x, name, go_backwards=False):
 
 
 def crnn_features(weights, crops):
-    """crops: (B,31,200) or (B,31,200,1) float32 in [0,1].  Returns bn_7 output (B,50,7,512) NHWC."""
+    """crops: (B,31,200), (B,31,200,1) or -- color model -- (B,31,200,3) float32 in [0,1].  Returns bn_7's output (B,512,50,7)."""
     w = _t(weights)
     x = torch.as_tensor(np.asarray(crops), dtype=torch.float32)
-    if x.dim() == 4:
-        x = x[..., 0]
-    # Permute((2,1,3)) then reverse axis 2 (recognition.py:215-216): (B,200,31), x[b,t,j] = crop[b,30-j,t]
-    x = torch.flip(x.permute(0, 2, 1), [2]).unsqueeze(1).contiguous()   # NCHW with H=200, W=31
+    if x.dim() == 3:
+        x = x[..., None]                                  # gray crops (B,31,200) -> one channel
+    # Permute((2,1,3)) then reverse axis 2 (recognition.py:215-216): (B,200,31,C), x[b,t,j] = crop[b,30-j,t];
+    # C = 1, or 3 for build_model(color=True) (recognition.py:214)
+    x = torch.flip(x.permute(0, 2, 1, 3), [2]).permute(0, 3, 1, 2).contiguous()   # NCHW with H=200, W=31
     x = _conv_relu(w, x, "conv_1", 3)
     x = _conv_relu(w, x, "conv_2", 3)
     x = _conv_relu(w, x, "conv_3", 3)

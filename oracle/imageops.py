@@ -186,7 +186,8 @@ def warp_box(gray, box, target_height=31, target_width=200, return_transform=Fal
     dst = np.array([[0, 0], [scale * w, 0], [scale * w, scale * h], [0, scale * h]]).astype("float32")
     M = cv2.getPerspectiveTransform(src=box, dst=dst)
     crop = cv2.warpPerspective(gray, M, dsize=(int(scale * w), int(scale * h)))
-    full = np.zeros((target_height, target_width), dtype="uint8")
+    # tools.py:108-113: a 3-channel image keeps its channels (color recognizer), a gray one stays 2-D
+    full = np.zeros((target_height, target_width) + gray.shape[2:], dtype="uint8")
     full[: crop.shape[0], : crop.shape[1]] = crop
     if return_transform:
         return full, M

@@ -11,7 +11,8 @@ from . import craft, crnn, imageops
 
 
 class OraclePipeline:
-    def __init__(self, craft_weights, crnn_weights, scale=2, max_size=2048):
+    def __init__(self, craft_weights, crnn_weights, scale=2, max_size=2048, color=False):
+        self.color = color                                   # recognizer built with color=True: crops keep their RGB channels
         self.craft_weights = {k: torch.as_tensor(np.asarray(v), dtype=torch.float32) for k, v in craft_weights.items()}
         self.crnn_weights = crnn_weights
         self.scale = scale
@@ -31,7 +32,7 @@ class OraclePipeline:
     def crops(self, images, box_groups):
         out = []
         for image, boxes in zip(images, box_groups):
-            gray = imageops.rgb_to_gray(image)
+            gray = image if self.color else imageops.rgb_to_gray(image)       # recognition.py:508-510
             for box in boxes:
                 out.append(imageops.warp_box(gray, box))
         return out

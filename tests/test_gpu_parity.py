@@ -379,6 +379,49 @@ def test_recognizer_without_spatial_transformer(cuda_device):
         Recognizer(weights=full, build_params={"color": True})
 
 
+def test_color_recognizer(cuda_device):
+    """build_model(color=True) (recognition.py:214, 508-510): RGB crops, no gray conversion, 3-channel conv_1.
+    b2o_warp_boxes_color == cv2.warpPerspective on the RGB image (every channel, <= 1 level on <= 0.1 % of the pixels as
+    for gray crops); logits against the fp32 oracle fed the same crops; the full pipeline with a color recognizer
+    against the oracle chain built the same way."""
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import crnn, imageops, synth
+    from oracle.pipeline import OraclePipeline
+    w = W.synthetic_crnn_weights(6, color=True)
+    assert w["conv_1.kernel"].shape == (3, 3, 3, 64)
+    rec = Recognizer(weights=w, build_params={"color": True})
+    rec.keep_workspace = True
+    rng = np.random.default_rng(23)
+    image = np.stack([synth.noise_gray(rng, 240, 320) for _ in range(3)], -1)          # three independent channels
+    quads = synth.random_quads(rng, 12, 240, 320, min_side=16, max_side=150)
+    img_t = torch.from_numpy(image[None]).to(cuda_device)
+    idx = torch.zeros(len(quads), dtype=torch.int32, device=cuda_device)
+    crnn_in, crops = rec.warp_device(img_t, torch.from_numpy(quads).to(cuda_device), idx, want_crops=True)
+    ref = np.stack([imageops.warp_box(image, q) for q in quads])
+    assert crops.shape == ref.shape == (12, 31, 200, 3)
+    diff = np.abs(crops.cpu().numpy().astype(np.int16) - ref.astype(np.int16))
+    assert diff.max() <= 1 and (diff > 0).mean() <= 1e-3
+    x = torch.empty_like(crnn_in)
+    rec.ctx.crops_to_input(crops.data_ptr(), 12, x.data_ptr(), _stream(), color=True)
+    assert torch.equal(x, crnn_in)                                  # both routes to the CRNN input agree bit for bit
+    texts = rec.recognize_crops(ref)
+    logits = rec.tap("logits", (12, 48, 37), torch.float32).cpu()
+    with torch.no_grad():
+        probs, inter = crnn.crnn_logits(w, ref.astype(np.float32) / 255, return_intermediates=True)
+    assert float((logits - inter["logits"]).abs().max()) <= 0.15
+    assert texts == crnn.labels_to_text(crnn.ctc_greedy(torch.softmax(logits, -1)))
+    assert rec.recognize(ref[0]) == texts[0]                        # single-crop API keeps the colour channels
+    with pytest.raises(ValueError):
+        Recognizer(weights=w)                                       # a 3-channel conv_1 needs color=True
+    cw = W.synthetic_craft_weights(3, textlike=True)
+    pages, _ = synth.text_images(seed=21, n=2, h=192, w=384, n_words=4)
+    got = Pipeline(detector=Detector(weights=cw), recognizer=rec, scale=2).recognize(pages)
+    want = OraclePipeline(cw, w, scale=2, color=True).recognize(pages)
+    assert [len(g) for g in got] == [len(r) for r in want] and sum(len(g) for g in got) >= 6
+
+
 def test_recognize_from_boxes_with_caller_supplied_quads(recognizer):
     """tools.warpBox on quads that are NOT rectangles (reference tools.py:88-95: minimum rotated rectangle first) and on a
     degenerate box (ZeroDivisionError, tools.py:95): the host rectification of ``recognize_from_boxes`` + the CUDA warp
