@@ -87,6 +87,16 @@ int b2o_resize_pad(b2o_ctx* ctx, const uint8_t* src_dev, int hs, int ws, int hr,
 int b2o_resize_pad_batch(b2o_ctx* ctx, const uint8_t* src_dev, int n, int hs, int ws, int hr, int wr,
                          uint8_t* dst_dev, int hp, int wp, uint8_t* gray_dev, void* stream);
 
+/* tools.read for JPEG input (tools.py:19-38: cv2.imread / cv2.imdecode + BGR->RGB) decoded on the GPU by nvJPEG, so
+ * that only the compressed file crosses PCIe.  b2o_jpeg_info parses the header (host only); b2o_decode_jpeg writes
+ * (height, width, 3) uint8 interleaved RGB at rgb_dev (gray files are expanded to three equal channels, as
+ * cv2.imread's default flag does).  nvJPEG is opened with dlopen on first use: B2O_ERR_STATE if the box has none,
+ * B2O_ERR_ARG for a stream it refuses (the caller then decodes that file on the host).  Pixels can differ from
+ * libjpeg-turbo's by a few levels (IDCT / chroma upsampling); tests/test_gpu_parity.py states the bound.       */
+int b2o_jpeg_info(b2o_ctx* ctx, const uint8_t* data_host, size_t size, int* height, int* width, int* components);
+int b2o_decode_jpeg(b2o_ctx* ctx, const uint8_t* data_host, size_t size, uint8_t* rgb_dev, int height, int width,
+                    void* stream);
+
 /* cv2.cvtColor(RGB2GRAY) (recognition.py:510) for a whole (n,h,w,3) batch -> (n,h,w).         */
 int b2o_rgb_to_gray(b2o_ctx* ctx, const uint8_t* img_dev, int n, int h, int w, uint8_t* gray_dev,
                     void* stream);

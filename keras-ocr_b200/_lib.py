@@ -42,6 +42,8 @@ SIGNATURES = {
     "b2o_load_crnn": (_i, [_vp, _c.POINTER(_Tensor), _i]),
     "b2o_resize_pad": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _i, _i, _i, _vp]),
     "b2o_resize_pad_batch": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "b2o_jpeg_info": (_i, [_vp, _vp, _sz, _c.POINTER(_i), _c.POINTER(_i), _c.POINTER(_i)]),
+    "b2o_decode_jpeg": (_i, [_vp, _vp, _sz, _vp, _i, _i, _vp]),
     "b2o_rgb_to_gray": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
     "b2o_craft_workspace_bytes": (_sz, [_i, _i, _i]),
     "b2o_craft_forward": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _sz, _vp]),
@@ -159,6 +161,17 @@ class Context:
     def resize_pad_batch(self, src, n, hs, ws, hr, wr, dst, hp, wp, gray, stream):
         self._check(self.lib.b2o_resize_pad_batch(self.handle, src, n, hs, ws, hr, wr, dst, hp, wp, gray, stream),
                     "b2o_resize_pad_batch")
+
+    def jpeg_info(self, data):
+        """(height, width, components) of a JPEG byte string, or None if nvJPEG is missing / refuses the stream."""
+        buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+        h, w, c = _i(), _i(), _i()
+        rc = self.lib.b2o_jpeg_info(self.handle, buf, len(data), ctypes.byref(h), ctypes.byref(w), ctypes.byref(c))
+        return (h.value, w.value, c.value) if rc == 0 else None
+
+    def decode_jpeg(self, data, rgb, h, w, stream):
+        buf = (ctypes.c_ubyte * len(data)).from_buffer_copy(data)
+        return self.lib.b2o_decode_jpeg(self.handle, buf, len(data), rgb, h, w, stream) == 0
 
     def rgb_to_gray(self, img, n, h, w, gray, stream):
         self._check(self.lib.b2o_rgb_to_gray(self.handle, img, n, h, w, gray, stream), "b2o_rgb_to_gray")

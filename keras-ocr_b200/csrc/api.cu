@@ -257,6 +257,7 @@ extern "C" void b2o_destroy(b2o_ctx* ctx) {
     DeviceGuard guard(ctx->device);
     for (void* p : ctx->owned) cudaFree(p);
     for (cudaEvent_t e : ctx->prof_events) cudaEventDestroy(e);
+    jpeg_release(ctx);
   }
   delete ctx;
 }

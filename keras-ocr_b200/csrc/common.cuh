@@ -115,8 +115,11 @@ struct b2o_ctx {
   bool profile = false;
   std::vector<cudaEvent_t> prof_events;   // (start, stop) pairs
   double prof_flop = 0.0;
+  void* jpeg = nullptr;        // nvJPEG handle + state, created on first use (jpeg.cu)
+  bool jpeg_failed = false;    // nvJPEG could not be opened on this box: do not try again
   void set_error(const std::string& e) { error = e; }
 };
+void jpeg_release(b2o_ctx* ctx);
 
 // CRAFT tail fused into the epilogue of a 16-channel tensor-core layer: conv_cls.6 (1x1 16->16, ReLU) and conv_cls.8
 // (1x1 16->2) on the 16 channels a thread already holds; fp32 (text, link) scores out (detection.py:404-410).

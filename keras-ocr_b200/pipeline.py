@@ -20,7 +20,7 @@ class Pipeline:
     (counts, boxes, labels).
     """
 
-    def __init__(self, detector=None, recognizer=None, scale=2, max_size=2048, inflight=1):
+    def __init__(self, detector=None, recognizer=None, scale=2, max_size=2048, inflight=1, gpu_decode=False):
         if detector is None:
             detector = detection.Detector()
         if recognizer is None:
@@ -36,6 +36,10 @@ class Pipeline:
         # Measured on the 32-page bench: ~2 % faster device-resident, but the half-size recurrent / box kernels
         # lose what the overlap gains and the end-to-end number does not move, hence the default of 1.
         self.inflight = inflight
+        # gpu_decode: JPEG files / buffers in ``images`` are decoded by nvJPEG into device memory (tools.read_device)
+        # instead of cv2 on the host (reference tools.py:19-38); pixels may differ from libjpeg's by a few levels, which is
+        # why it is opt-in for a drop-in.
+        self.gpu_decode = gpu_decode
         self.min_chunk = 4
         self.last_stats = {}
         self._h2d_stream = None
@@ -98,9 +102,13 @@ class Pipeline:
                                      hp, wp, gray.data_ptr(), stream)
         else:
             for i, image in enumerate(images):
-                assert image.ndim == 3 and image.shape[2] == 3 and image.dtype == np.uint8, "images must be HxWx3 uint8"
-                src = self._upload(image)
-                h2d += src.numel()
+                if isinstance(image, torch.Tensor):                # decoded on the device (gpu_decode) or supplied resident
+                    assert image.is_cuda and image.dim() == 3 and image.shape[2] == 3 and image.dtype == torch.uint8
+                    src = image.contiguous()
+                else:
+                    assert image.ndim == 3 and image.shape[2] == 3 and image.dtype == np.uint8, "images must be HxWx3 uint8"
+                    src = self._upload(image)
+                    h2d += src.numel()
                 _, hr, wr = plans[i]
                 det.ctx.resize_pad(src.data_ptr(), image.shape[0], image.shape[1], hr, wr, batch.data_ptr(), i, hp, wp, stream)
         self.last_stats["h2d_bytes"] = self.last_stats.get("h2d_bytes", 0) + int(h2d)
@@ -157,7 +165,10 @@ class Pipeline:
         the coordinates of the *input* image.
         """
         if not isinstance(images, (np.ndarray, torch.Tensor)):
-            images = [tools.read(image) for image in images]
+            if self.gpu_decode and self._native():
+                images = [tools.read_device(image, self.detector.ctx, self.detector.device) for image in images]
+            else:
+                images = [tools.read(image) for image in images]
         if detection_kwargs is None:
             detection_kwargs = {}
         if recognition_kwargs is None:
@@ -200,7 +211,10 @@ class Pipeline:
         assert self._native(), "recognize_records needs this package's Detector and Recognizer"
         assert len(self.recognizer.alphabet) + 1 <= 127, "record labels travel as int8: alphabets up to 126 characters"
         if not isinstance(images, (np.ndarray, torch.Tensor)):
-            images = [tools.read(image) for image in images]
+            if self.gpu_decode:
+                images = [tools.read_device(image, self.detector.ctx, self.detector.device) for image in images]
+            else:
+                images = [tools.read(image) for image in images]
         thresholds = {k: v for k, v in (detection_kwargs or {}).items()
                       if k in ("detection_threshold", "text_threshold", "link_threshold", "size_threshold")}
         n = len(images)

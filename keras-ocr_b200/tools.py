@@ -26,6 +26,33 @@ def read(filepath_or_buffer: typing.Union[str, io.BytesIO, np.ndarray]):
     return cv2.cvtColor(image, cv2.COLOR_BGR2RGB)
 
 
+def read_device(filepath_or_buffer, ctx, device):
+    """``read`` with the decode on the GPU where possible: a JPEG file / buffer is handed to nvJPEG
+    through ``b2o_decode_jpeg`` and comes back as an (H, W, 3) uint8 RGB CUDA tensor -- only the compressed bytes cross
+    PCIe.  Everything else (arrays, PNG, JPEG flavours nvJPEG refuses, a box without nvJPEG) goes through ``read`` and is
+    returned as the host array the caller uploads as before."""
+    import torch
+
+    if isinstance(filepath_or_buffer, (np.ndarray, torch.Tensor)):
+        return filepath_or_buffer
+    if isinstance(filepath_or_buffer, str):
+        assert os.path.isfile(filepath_or_buffer), "Could not find image at path: " + filepath_or_buffer
+        with open(filepath_or_buffer, "rb") as f:
+            data = f.read()
+    elif hasattr(filepath_or_buffer, "read"):
+        data = filepath_or_buffer.read()
+    else:
+        raise TypeError(f"cannot read image from {type(filepath_or_buffer)!r}")
+    if data[:2] == b"\xff\xd8":                                  # JPEG start-of-image marker
+        info = ctx.jpeg_info(data)
+        if info is not None and info[2] in (1, 3):
+            h, w, _ = info
+            out = torch.empty((h, w, 3), dtype=torch.uint8, device=device)
+            if ctx.decode_jpeg(data, out.data_ptr(), h, w, torch.cuda.current_stream(device).cuda_stream):
+                return out
+    return read(io.BytesIO(data))
+
+
 def resize_plan(shape, max_scale, max_size):
     """The scale and output size tools.resize_image (reference tools.py:378-398) would pick.
 

@@ -376,7 +376,52 @@ def test_recognizer_without_spatial_transformer(cuda_device):
     with pytest.raises(ValueError):
         Recognizer(weights=w)                                        # stn=True (default) needs the transformer's tensors
     with pytest.raises(NotImplementedError):
-        Recognizer(weights=full, build_params={"color": True})
+        Recognizer(weights=full, build_params={"rnn_units": (64, 64)})   # other architectures are not implemented
+
+
+def test_gpu_jpeg_decode(cuda_device, tmp_path):
+    """tools.read on the GPU: nvJPEG through b2o_decode_jpeg against cv2.imdecode (= what the reference's
+    tools.read returns, tools.py:19-38).  The two decoders are not bit-identical (IDCT rounding, chroma upsampling):
+    4:4:4 and gray files agree to <= 2 levels, 4:2:0 files to <= 6 levels at sharp colour edges with a mean difference
+    below 0.5 level; the pipeline then finds the same words from paths decoded on the GPU as from host-decoded arrays."""
+    import cv2
+    from keras_ocr_b200 import tools
+    from keras_ocr_b200.detection import Detector
+    from keras_ocr_b200.pipeline import Pipeline
+    from keras_ocr_b200.recognition import Recognizer
+    from oracle import synth
+    ctx = _lib.Context(0)
+    pages, _ = synth.text_images(seed=41, n=2, h=192, w=384, n_words=4)
+    if ctx.jpeg_info(cv2.imencode(".jpg", pages[0])[1].tobytes()) is None:
+        pytest.skip("nvJPEG not available on this box")
+    rng = np.random.default_rng(3)
+    photo = cv2.GaussianBlur(rng.integers(0, 256, (120, 200, 3)).astype(np.float32), (0, 0), 3).clip(0, 255).astype(np.uint8)
+    cases = {"text_420": (pages[0], [cv2.IMWRITE_JPEG_QUALITY, 95]),
+             "photo_444": (photo, [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]),
+             "gray": (cv2.cvtColor(photo, cv2.COLOR_RGB2GRAY), [cv2.IMWRITE_JPEG_QUALITY, 90])}
+    for tag, (img, params) in cases.items():
+        data = cv2.imencode(".jpg", img[..., ::-1] if img.ndim == 3 else img, params)[1].tobytes()
+        host = tools.read(__import__("io").BytesIO(data))
+        dev = tools.read_device(__import__("io").BytesIO(data), ctx, cuda_device)
+        assert isinstance(dev, torch.Tensor) and dev.is_cuda and tuple(dev.shape) == host.shape, tag
+        diff = np.abs(dev.cpu().numpy().astype(np.int16) - host.astype(np.int16))
+        print(f"jpeg {tag}: max {diff.max()} mean {diff.mean():.3f}")
+        assert diff.max() <= (6 if tag == "text_420" else 2) and diff.mean() <= 0.5, (tag, int(diff.max()), float(diff.mean()))
+    png = str(tmp_path / "p.png")                                  # not a JPEG: host decode, returned as an array
+    cv2.imwrite(png, pages[1][..., ::-1])
+    assert isinstance(tools.read_device(png, ctx, cuda_device), np.ndarray)
+    paths = []
+    for i, page in enumerate(pages):
+        paths.append(str(tmp_path / f"page{i}.jpg"))
+        cv2.imwrite(paths[-1], page[..., ::-1], [cv2.IMWRITE_JPEG_QUALITY, 95])
+    det = Detector(weights=W.synthetic_craft_weights(3, textlike=True))
+    rec = Recognizer(weights=W.synthetic_crnn_weights(2))
+    on_gpu = Pipeline(detector=det, recognizer=rec, scale=2, gpu_decode=True).recognize(paths)
+    on_host = Pipeline(detector=det, recognizer=rec, scale=2).recognize(paths)
+    assert [len(g) for g in on_gpu] == [len(g) for g in on_host] and sum(len(g) for g in on_host) >= 6
+    for g, h in zip(on_gpu, on_host):
+        for (_, bg), (_, bh) in zip(g, h):
+            assert np.abs(bg - bh).max() <= 1.0                    # a few grey levels do not move a box by a pixel
 
 
 def test_color_recognizer(cuda_device):
