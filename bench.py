@@ -46,7 +46,8 @@ def workload_config(n_gpus):
         "pages_per_gpu": PAGES_PER_RANK, "global_batch": PAGES_PER_RANK * n_gpus,
         "source": f"{PAGE_H}x{PAGE_W}x3 uint8, {WORDS_PER_PAGE} cv2.putText words/page",
         "detector_input": "1536x1536", "scale": SCALE, "parallelism": f"dp{n_gpus}",
-        "weights": "seeded synthetic (CRAFT textlike routing, CRNN random); no pretrained files offline",
+        "weights": "no pretrained files offline: CRAFT seeded synthetic with textlike routing; CRNN seeded backbone + head fitted "
+                   "on the rendered pages (oracle/train_crnn_head.py) -- the words found are the rendered words",
         "l2": "per-step activations (>40 GB) exceed the 126 MB L2; no explicit flush needed",
     }
 
@@ -122,7 +123,7 @@ def cpu_sample(threads=None, n_images=1, rank=0):
         torch.set_num_threads(threads)
     cores = torch.get_num_threads()
     pages = make_pages(rank)[:n_images]
-    pipe = OraclePipeline(W.synthetic_craft_weights(3, textlike=True), W.synthetic_crnn_weights(2), scale=SCALE)
+    pipe = OraclePipeline(W.synthetic_craft_weights(3, textlike=True), W.synthetic_crnn_weights(2, decisive=True), scale=SCALE)
     t0 = time.perf_counter()
     out = pipe.recognize(pages)
     dt = time.perf_counter() - t0
@@ -198,7 +199,7 @@ def run_b200(args):
     from keras_ocr_b200.recognition import Recognizer
 
     det = Detector(weights=W.synthetic_craft_weights(3, textlike=True), device=local_rank)
-    rec = Recognizer(weights=W.synthetic_crnn_weights(2), device=local_rank)
+    rec = Recognizer(weights=W.synthetic_crnn_weights(2, decisive=True), device=local_rank)
     pipe = Pipeline(detector=det, recognizer=rec, scale=SCALE, max_size=2048)
     pages = make_pages(rank)
     pages_dev = torch.from_numpy(pages).to(device)

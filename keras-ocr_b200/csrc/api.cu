@@ -240,7 +240,8 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
   if (const char* e = getenv("B2O_TC_ISSUERS")) ctx->tc_issuers = (atoi(e) == 2) ? 2 : (atoi(e) == 1 ? 1 : 0);
-  if (const char* e = getenv("B2O_TC_BOX16")) ctx->tc_box16 = atoi(e) != 0;
+  if (const char* e = getenv("B2O_TC_BOX16")) { const int v = atoi(e); ctx->tc_box16 = v == 0 ? 0 : (v == 10 ? 10 : 16); ctx->tc_box_forced = v != 0; }
+  if (const char* e = getenv("B2O_TC_BOX_ALL")) ctx->tc_box_all = atoi(e) != 0;
   if (const char* e = getenv("B2O_UPCONV_COMMUTE")) ctx->no_commute = atoi(e) == 0;      // 1: commuted decoder upsampling (opt-in, see common.cuh)
   if (const char* e = getenv("B2O_FUSED_TAIL")) ctx->no_fused_tail = atoi(e) == 0;      // 0: separate head_tail_kernel (A/B, tests)
   if (const char* e = getenv("B2O_TC_PAIR")) {        // default 1; 0 = single-CTA tiles (A/B runs); 2 = generic tiles too

@@ -88,7 +88,9 @@ struct b2o_ctx {
   int conv_engine = B2O_CONV_AUTO;
   int tc_issuers = 0;          // MMA-issuing warps of conv_tc_kernel: 0 = auto (2 for N <= 128 tiles), 1, 2
   bool tc_pair = true;         // CTA pairs (tcgen05 cta_group::2) for the halo-tile layers; B2O_TC_PAIR=0 turns them off
-  bool tc_box16 = true;        // one 16 x 18 A box per K chunk in MODE 3 layers (B2O_TC_BOX16=0: three 8 x 18 boxes)
+  int tc_box16 = 16;           // width of the single A box per K chunk in MODE 3 layers (B2O_TC_BOX16=0: three 8 x 18 boxes; 10: tile + halo only)
+  bool tc_box_forced = false;  // B2O_TC_BOX16 was given: use that width everywhere instead of the per-layer rule
+  bool tc_box_all = false;     // B2O_TC_BOX_ALL=1: single-box tiles for every grouped layer (default: N <= 64 with 64-/32-channel chunks)
   bool tc_pair_generic = false;   // B2O_TC_PAIR=2: also pair the generic tiles (1x1 / dilated layers): bit-identical, no gain measured (profiles/r2a_ab_pair2.log)
   // Decoder glue: B2O_UPCONV_COMMUTE=1 commutes the 2x upsampling behind the decoder half of upconvN.conv.0 (low-res GEMM +
   // upsample-add in the full-resolution layer's epilogue).  Numerically validated, but measured SLOWER on B200

@@ -375,7 +375,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   const int cta = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
   const int ncta = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   const int pair_shift = PAIR ? 1 : 0;                     // tile column = (pair column << 1) + rank
-  constexpr int TAP_SHIFT = (BOX16 ? 32 : 16) * KCH;       // bytes between the tile's image rows in an A stage (= SBO)
+  // bytes between the tile's image rows in an A stage (= the descriptor's stride between 8-row groups): 8 pixels with three
+  // boxes per K chunk; with the single box its width p.box16 (10 = just the tile + halo, or 16 = whole 1 KB swizzle atoms
+  // per row).  Rows need not start on an atom boundary: the swizzle is a function of the absolute address (probe).
+  const int TAP_SHIFT = BOX16 ? p.box16 * 2 * KCH : 16 * KCH;
   constexpr int KSTEPS = KCH / UMMA_K;
   // TMEM accumulator stages: as many as fit in the 512 columns (max 8).  With only two, a short-K tile is
   // bound by the *latency* of the epilogue hand-off (tmem_full -> LDTM -> stores -> tmem_empty), not by its
@@ -544,9 +547,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
     // (The code is written for NUM_ISSUERS warps taking alternate A stages; see the note at NUM_ISSUERS.)
     constexpr uint32_t idesc = (1u << 4) | (static_cast<uint32_t>(BLOCK_N >> 3) << 17) |
                                (static_cast<uint32_t>((PAIR ? 2 * BLOCK_M : BLOCK_M) >> 4) << 24);   // D=f32, A=B=f16 K-major, N, M=128 (256 per pair)
-    constexpr uint32_t TAP_DESC = TAP_SHIFT >> 4, B_DESC = B_BYTES >> 4;       // in 16-byte descriptor units
+    const uint32_t TAP_DESC = static_cast<uint32_t>(TAP_SHIFT) >> 4;          // in 16-byte descriptor units
+    constexpr uint32_t B_DESC = B_BYTES >> 4;
     const int me = warp - 1;
-    const uint64_t a_desc0 = umma_desc<KCH, TAP_SHIFT>(smem_u32(smem_a));
+    // (stride field bits [32,46) re-written for the run-time row pitch of the single-box tiles)
+    const uint64_t a_desc0 = (umma_desc<KCH, 16 * KCH>(smem_u32(smem_a)) & ~(static_cast<uint64_t>(0x3FFF) << 32)) |
+                             (static_cast<uint64_t>(static_cast<uint32_t>(TAP_SHIFT) >> 4) << 32);
     const uint64_t b_desc0 = umma_desc<KCH>(smem_u32(smem_b));
     const uint32_t a_step = static_cast<uint32_t>(p.a_stride) >> 4;
     if (RESIDENT) { mbar_wait(res_full, 0); tcgen05_after_sync(); }
@@ -1088,9 +1094,13 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   // (conv2 64->64 4.66 -> 4.31 ms, upconv4.3 1.12 -> 0.86, conv_cls.0/.2 0.64 -> 0.57), N = 128 tiles lose 3-5 % (fewer,
   // larger ring slots) and the 16-channel stem loses 14 % (32-byte pixel rows: the dx-shifted operand reads straddle
   // the 256-byte swizzle atoms) -- so only the former use it.
-  if (ctx->tc_box16 && p.resident && bn <= 64 && kch >= 32 && ctx->conv_engine == B2O_CONV_AUTO) {
-    const int a16 = 18 * 16 * kch * 2;                     // 36864 / 18432 / 9216 B: whole 1 KB units for every swizzle mode
-    if ((budget - res_bytes) / a16 >= 2 * kchunks) { p.box16 = 1; p.a_bytes = a16; p.a_stride = a16; }
+  if (ctx->tc_box16 && p.resident && (ctx->tc_box_all || (bn <= 64 && kch >= 32)) && bn <= 128 && ctx->conv_engine == B2O_CONV_AUTO) {
+    // box width in pixels: 10 (just the tile + halo) for 64-channel chunks, 16 (image rows on whole swizzle atoms) for
+    // 32-channel chunks -- measured (profiles/r2g_box_width.txt): width 10 cuts conv2's DRAM re-reads (11.9 -> 10.4 GB) and
+    // gains on conv2 / upconv4.3, but loses 19-25 % on the 64-byte-row conv_cls layers; B2O_TC_BOX16=10|16 forces one
+    const int bw = ctx->tc_box_forced ? ctx->tc_box16 : (kch == 64 ? 10 : 16);
+    const int a1 = 18 * bw * kch * 2, a1s = (a1 + 1023) / 1024 * 1024;
+    if ((budget - res_bytes) / a1s >= 2 * kchunks) { p.box16 = bw; p.a_bytes = a1; p.a_stride = a1s; }
   }
   if (p.resident) {
     p.na = static_cast<int>((budget - res_bytes) / p.a_stride);
@@ -1153,7 +1163,7 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   cuuint64_t strides[3] = {static_cast<cuuint64_t>(in.ld) * 2, static_cast<cuuint64_t>(in.ld) * 2 * in.w,
                            static_cast<cuuint64_t>(in.ld) * 2 * in.w * in.h};
   cuuint32_t box[4] = {static_cast<cuuint32_t>(kch), 1u << p.bw_log2, 1u << p.bh_log2, 1u << p.bn_log2};
-  if (p.halo) { box[1] = p.box16 ? 16 : 8; box[2] = 18; box[3] = 1; }
+  if (p.halo) { box[1] = p.box16 ? p.box16 : 8; box[2] = 18; box[3] = 1; }
   cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(&amap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, in.ptr, dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kch), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -24,7 +24,7 @@ VAR, OFF, ON = (sys.argv[1:4] + ["B2O_TC_PAIR", "0", "1"][len(sys.argv) - 1:])[:
 def make(on):
     os.environ[VAR] = ON if on else OFF
     det = Detector(weights=W.synthetic_craft_weights(3, textlike=True))
-    rec = Recognizer(weights=W.synthetic_crnn_weights(2))
+    rec = Recognizer(weights=W.synthetic_crnn_weights(2, decisive=True))
     os.environ.pop(VAR, None)
     return Pipeline(detector=det, recognizer=rec, scale=2)
 

@@ -6,7 +6,9 @@ from keras_ocr_b200 import _lib
 ctx = _lib.Context(0)
 lib = ctx.lib
 lib.b2o_debug_read_tc.argtypes = [ctypes.POINTER(ctypes.c_ulonglong), ctypes.c_int]
-cases = [("stem 16->64 3x3", 8, 1536, 1536, 16, 64, 3), ("conv2 64->64 3x3", 8, 1536, 1536, 64, 64, 3), ("cls 32->32 3x3", 8, 768, 768, 32, 32, 3),
+cases = [("crnn conv_6 512->512", 256, 50, 7, 512, 512, 3), ("crnn conv_4 256->256", 256, 100, 15, 256, 256, 3),
+         ("slice5.2 1x1 1024", 32, 96, 96, 1024, 1024, 1),
+         ("stem 16->64 3x3", 8, 1536, 1536, 16, 64, 3), ("conv2 64->64 3x3", 8, 1536, 1536, 64, 64, 3), ("cls 32->32 3x3", 8, 768, 768, 32, 32, 3),
          ("conv3 64->128", 8, 768, 768, 64, 128, 3), ("conv4 128->128", 8, 768, 768, 128, 128, 3),
          ("256->256", 8, 384, 384, 256, 256, 3), ("1x1 64->64", 8, 1536, 1536, 64, 64, 1)]
 rng = np.random.default_rng(0)

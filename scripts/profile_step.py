@@ -23,7 +23,7 @@ def main():
     pages_n = int(os.environ.get("PAGES", 32))
     pages, _ = synth.text_images(seed=1000, n=pages_n, h=768, w=768, n_words=32)
     pipe = Pipeline(detector=Detector(weights=W.synthetic_craft_weights(3, textlike=True)),
-                    recognizer=Recognizer(weights=W.synthetic_crnn_weights(2)), scale=2)
+                    recognizer=Recognizer(weights=W.synthetic_crnn_weights(2, decisive=True)), scale=2)
     dev = torch.from_numpy(pages).cuda()
     for _ in range(2):
         out = pipe.recognize(dev)
