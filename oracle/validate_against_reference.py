@@ -264,7 +264,7 @@ def check_crnn(out):
     alphabet = "0123456789abcdefghijklmnopqrstuvwxyz"
     shim.reset()
     backbone, model, training_model, prediction_model = scope["build_model"](alphabet=alphabet, **params)
-    wts = W.synthetic_crnn_weights(seed=2)
+    wts = W.synthetic_crnn_weights(seed=2, decisive=True)      # seeded backbone + the head fitted on rendered words
     used = shim.load_weights(wts)
     assert used == set(wts), sorted(set(wts) - used)          # every tensor found its layer, by the reference's names
 
@@ -280,12 +280,17 @@ def check_crnn(out):
     assert np.abs(ref[0, -1]).max() < 1e-5 and np.abs(ref[0, :, -1]).max() < 1e-5   # identity theta: last row / column cancel to 0
     out["stn_features"], out["stn_theta"], out["stn_out"] = feat, theta, ref.astype(np.float32)
 
-    # (2) the whole recognizer on rendered word crops + noise crops
+    # (2) the whole recognizer on noise crops + the word crops the oracle pipeline cuts out of two rendered pages
+    from oracle.pipeline import OraclePipeline
     gray = synth.noise_gray(rng, 31, 200 * 3)
     crops = np.stack([gray[:, i * 200:(i + 1) * 200] for i in range(3)])
-    words, _ = synth.text_images(seed=9, n=1, h=62, w=400, n_words=2)
-    word_crop = cv2.resize(cv2.cvtColor(words[0], cv2.COLOR_RGB2GRAY), (200, 31))
-    crops = np.concatenate([crops, word_crop[None]]).astype(np.uint8)
+    pages, _ = synth.text_images(seed=21, n=2, h=192, w=384, n_words=4)
+    chain = OraclePipeline(W.synthetic_craft_weights(3, textlike=True), wts, scale=2)
+    batch, _ = chain.prepare(pages)
+    word_crops = np.array(chain.crops(batch, chain.detect(batch)))
+    assert len(word_crops) >= 6
+    crops = np.concatenate([crops, word_crops]).astype(np.uint8)
+    out["crnn_n_noise"] = np.array(3)
     x = (crops.astype("float32") / 255)[..., np.newaxis]                  # recognition.py:524-526
     probs_ref = model.predict(x).numpy()
     labels_ref = prediction_model.predict(x).numpy()
@@ -296,8 +301,10 @@ def check_crnn(out):
     e_p = float((probs - torch.from_numpy(probs_ref)).abs().max())
     print(f"  build_model (reference source on the shim) vs oracle: backbone max|diff| = {e_l2:.2e}, softmax {e_p:.2e}, "
           f"labels equal: {np.array_equal(labels, labels_ref)}")
-    assert probs_ref.shape == (4, 48, 37) and labels_ref.shape == (4, 48)
-    assert e_l2 < 1e-4 and e_p < 1e-4, (e_l2, e_p)
+    assert probs_ref.shape == (len(crops), 48, 37) and labels_ref.shape == (len(crops), 48)
+    # fp32 on both sides, different summation orders (torch.nn.LSTM vs the explicit gate loop); the fitted head's larger
+    # weights amplify that to ~1e-4 on the LSTM outputs in [-1, 1]
+    assert e_l2 < 5e-4 and e_p < 1e-4, (e_l2, e_p)
     assert np.array_equal(labels, labels_ref)
     out["crnn_crops"] = crops
     out["crnn_probs"] = probs_ref.astype(np.float32)

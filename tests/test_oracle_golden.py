@@ -99,15 +99,16 @@ def test_crnn_matches_reference_source_on_the_keras_shim(golden_dir):
     Pins the recognizer's wiring, the STN sampler and the CTC padding of the oracle; the per-layer arithmetic is the
     documented Keras semantics (TensorFlow is not installable offline)."""
     g = np.load(os.path.join(golden_dir, "crnn.npz"))
-    wts = W.synthetic_crnn_weights(seed=2)
+    wts = W.synthetic_crnn_weights(seed=2, decisive=True)
     out = crnn.stn_sample(torch.from_numpy(g["stn_features"]), torch.from_numpy(g["stn_theta"]))
     assert float(np.abs(out.numpy() - g["stn_out"]).max()) < 1e-4
     with torch.no_grad():
         probs = crnn.crnn_logits(wts, g["crnn_crops"].astype(np.float32) / 255)
-    assert probs.shape == g["crnn_probs"].shape == (4, 48, 37)
+    assert probs.shape == g["crnn_probs"].shape and probs.shape[1:] == (48, 37) and probs.shape[0] >= 9
     assert float(np.abs(probs.numpy() - g["crnn_probs"]).max()) < 1e-4
     assert np.array_equal(crnn.ctc_greedy(probs), g["crnn_labels"])
-    assert (g["crnn_labels"] >= 0).any()                              # the fixture really decodes characters
+    words = crnn.labels_to_text(g["crnn_labels"][int(g["crnn_n_noise"]):])
+    assert all(3 <= len(w) <= 10 for w in words), words                # the word crops decode to whole words
 
 
 def test_keras_shim_lstm_is_independent_of_the_oracle_loop():
