@@ -52,10 +52,30 @@ def workload_config(n_gpus):
     }
 
 
-def make_pages(rank):
+def make_pages(rank, with_layout=False):
     from oracle import synth
-    images, _ = synth.text_images(seed=1000 + rank, n=PAGES_PER_RANK, h=PAGE_H, w=PAGE_W, n_words=WORDS_PER_PAGE)
-    return images
+    if not with_layout:
+        images, _ = synth.text_images(seed=1000 + rank, n=PAGES_PER_RANK, h=PAGE_H, w=PAGE_W, n_words=WORDS_PER_PAGE)
+        return images
+    rng = np.random.default_rng(1000 + rank)                     # the same stream as text_images
+    laid = [synth.text_image(rng, PAGE_H, PAGE_W, WORDS_PER_PAGE, return_layout=True) for _ in range(PAGES_PER_RANK)]
+    return np.stack([p[0] for p in laid]), [p[1] for p in laid], [p[2] for p in laid]
+
+
+def words_read(result, words, rects):
+    """(rendered words found with the right text, rendered words): a (text, box) counts when the box centre lies in
+    exactly one rendered word's glyph rectangle and the text equals that word.  Outside the timed region: a
+    full-size sanity check of WHAT the benchmarked step produced, not only how fast."""
+    hit = 0
+    for group, page_words, page_rects in zip(result, words, rects):
+        found = set()
+        for text, box in group:
+            c = np.asarray(box).mean(0)
+            inside = [k for k, (x0, y0, x1, y1) in enumerate(page_rects) if x0 <= c[0] <= x1 and y0 <= c[1] <= y1]
+            if len(inside) == 1 and page_words[inside[0]] == text:
+                found.add(inside[0])
+        hit += len(found)
+    return hit, sum(len(w) for w in words)
 
 
 def measured_peaks():
@@ -201,7 +221,7 @@ def run_b200(args):
     det = Detector(weights=W.synthetic_craft_weights(3, textlike=True), device=local_rank)
     rec = Recognizer(weights=W.synthetic_crnn_weights(2, decisive=True), device=local_rank)
     pipe = Pipeline(detector=det, recognizer=rec, scale=SCALE, max_size=2048)
-    pages = make_pages(rank)
+    pages, page_words, page_rects = make_pages(rank, with_layout=True)
     pages_dev = torch.from_numpy(pages).to(device)
     # the e2e leg's inputs live in PINNED host memory (the contract's "from pinned host memory"); the numpy
     # view below is what the user-facing call receives, and Pipeline uploads an already-pinned array as is
@@ -290,6 +310,9 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
+    # what the benchmarked step produced, checked at full size on rank 0's pages (outside the timed region; the recognizer
+    # head is fitted on exactly these pages -- the other ranks' pages are only ever counted)
+    hit, rendered = words_read(pipe.recognize(pages_dev), page_words, page_rects)
     total_pages = PAGES_PER_RANK * world
     value = total_pages * args.steps / (ms_dev / 1e3)
     e2e_value = total_pages * args.steps / (ms_e2e / 1e3)
@@ -317,7 +340,10 @@ def run_b200(args):
                      "kernel_share_of_step": tc_ms / step_ms_plain if step_ms_plain > 0 else None,
                      "traffic": traffic},
         "words_per_step": stats["words"],
+        "words_read_correctly": {"rank0_pages": PAGES_PER_RANK, "rendered": rendered, "read": hit},
     }
+    if hit < 0.9 * rendered:                                # reported, never fatal: the line above is the measurement
+        sys.stderr.write(f"bench.py: only {hit} of {rendered} rendered words were read correctly\n")
     if world > 1:
         line["per_rank_ms_per_step"] = per_rank_dev
         line["rank0_decode_ms_per_step"] = round(decode_ms, 3)

@@ -92,7 +92,7 @@ int b2o_resize_pad_batch(b2o_ctx* ctx, const uint8_t* src_dev, int n, int hs, in
  * (height, width, 3) uint8 interleaved RGB at rgb_dev (gray files are expanded to three equal channels, as
  * cv2.imread's default flag does).  nvJPEG is opened with dlopen on first use: B2O_ERR_STATE if the box has none,
  * B2O_ERR_ARG for a stream it refuses (the caller then decodes that file on the host).  Pixels can differ from
- * libjpeg-turbo's (IDCT rounding: <= 2 levels; 4:2:0 chroma upsampling: up to ~25 levels at sharp colour edges, mean < 0.5);
+ * libjpeg-turbo's (IDCT rounding: <= 4 levels; 4:2:0 chroma upsampling: up to ~25 levels at sharp colour edges, mean < 0.5);
  * tests/test_gpu_parity.py::test_gpu_jpeg_decode states the bounds.                                             */
 int b2o_jpeg_info(b2o_ctx* ctx, const uint8_t* data_host, size_t size, int* height, int* width, int* components);
 int b2o_decode_jpeg(b2o_ctx* ctx, const uint8_t* data_host, size_t size, uint8_t* rgb_dev, int height, int width,

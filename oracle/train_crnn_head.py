@@ -8,7 +8,7 @@ the crops that the ORACLE pipeline cuts out of ``oracle.synth.text_images`` page
 those pages, so the parity tests can assert ``texts == oracle texts`` for every crop and, beyond parity, ``texts ==
 rendered words``.
 
-    python -m oracle.train_crnn_head            # ~25 min on 8 cores; writes keras-ocr_b200/data/crnn_hershey_head.npz
+    python -m oracle.train_crnn_head            # ~1.5 h on 8 cores; writes keras-ocr_b200/data/crnn_hershey_head.npz
 
 The model trained here is the restatement in ``oracle/crnn.py`` expressed with ``torch.nn.LSTM`` (Keras gate order
 i,f,c,o == torch's i,f,g,o; one bias; ``go_backwards`` outputs left in processing order, reference
@@ -33,6 +33,7 @@ from oracle.pipeline import OraclePipeline                      # noqa: E402
 OUT = os.path.join(ROOT, "keras-ocr_b200", "data", "crnn_hershey_head.npz")
 CACHE = os.environ.get("B2O_TRAIN_CACHE", "/tmp/b2o_train_cache")
 CRAFT_SEED, CRNN_SEED = 3, 2                                    # the seeds tests/ and bench.py use
+JITTER_COPIES = int(os.environ.get("B2O_TRAIN_JITTER", 4))      # perturbed-box copies of every training crop
 
 # (seed, n, h, w, n_words): every page set the GPU tests / smoke / bench render, plus extra pages for generalisation
 PAGE_SETS = [
@@ -43,9 +44,11 @@ PAGE_SETS = [
 HOLDOUT = (3000, 4, 768, 768, 32)
 
 
-def labelled_crops(page_set, craft_w, crnn_w, jitter=0, rng=None):
-    """Oracle chain up to the crops, each crop paired with the rendered word whose glyph rectangle holds the box
-    centre (None when a box does not sit on exactly one word, e.g. a split word)."""
+JITTER_PX = 3.0          # detector-input pixels: the fp16 CUDA chain's boxes differ from the oracle's by up to ~3 such pixels at 1536^2
+
+
+def detect_pages(page_set, craft_w, crnn_w):
+    """Oracle chain up to the boxes: (padded batch, scales, box groups, rendered words, glyph rectangles)."""
     seed, n, h, w, n_words = page_set
     r = np.random.default_rng(seed)
     pages, words, rects = [], [], []
@@ -57,6 +60,15 @@ def labelled_crops(page_set, craft_w, crnn_w, jitter=0, rng=None):
     groups = []
     for i in range(0, n, 4):                                    # bounded memory: 4 pages of fp32 CRAFT at a time
         groups += imageops.get_boxes(pipe.detect_scores(batch[i:i + 4]))
+    return batch, scales, groups, words, rects
+
+
+def labelled_crops(page_set, craft_w, crnn_w, jitter=0, rng=None, detected=None):
+    """Oracle chain up to the crops, each crop paired with the rendered word whose glyph rectangle holds the box
+    centre (None when a box does not sit on exactly one word, e.g. a split word).  ``jitter`` extra copies of every
+    crop are cut from the box with its corners moved by up to JITTER_PX: the recognizer must give the same string for
+    the slightly different boxes the fp16 chain finds."""
+    batch, scales, groups, words, rects = detected if detected is not None else detect_pages(page_set, craft_w, crnn_w)
     crops, labels = [], []
     for img, boxes, ws, rc, s in zip(batch, groups, words, rects, scales):
         gray = imageops.rgb_to_gray(img)
@@ -73,7 +85,7 @@ def labelled_crops(page_set, craft_w, crnn_w, jitter=0, rng=None):
             word = ws[k] if k is not None and counts[k] == 1 else None
             variants = [np.asarray(box, np.float32)]
             for _ in range(jitter):
-                variants.append(variants[0] + rng.uniform(-1.5, 1.5, (4, 2)).astype(np.float32))
+                variants.append(variants[0] + rng.uniform(-JITTER_PX, JITTER_PX, (4, 2)).astype(np.float32))
             for v in variants:
                 crops.append(imageops.warp_box(gray, v))
                 labels.append(word)
@@ -142,7 +154,7 @@ def main():
     t0 = time.time()
 
     def cached(tag, page_set, jitter):
-        path = os.path.join(CACHE, f"{tag}.npz")
+        path = os.path.join(CACHE, f"{tag}_j{jitter}.npz")
         if os.path.exists(path):
             d = np.load(path, allow_pickle=True)
             return torch.from_numpy(d["seq"]), list(d["labels"])
@@ -154,7 +166,7 @@ def main():
 
     seqs, labels = [], []
     for ps in PAGE_SETS:
-        s, l = cached("set_%d" % ps[0], ps, jitter=1)
+        s, l = cached("set_%d" % ps[0], ps, jitter=JITTER_COPIES)
         seqs.append(s); labels += l
     seq = torch.cat(seqs)
     keep = [i for i, l in enumerate(labels) if l is not None]
@@ -163,9 +175,19 @@ def main():
     print(f"train {len(y_train)} crops, holdout {len(y_hold)}", flush=True)
 
     head = Head()
+    if os.path.exists(OUT) and os.environ.get("B2O_TRAIN_WARM", "1") != "0":      # warm start from the previous fit
+        prev = np.load(OUT)
+        with torch.no_grad():
+            head.fc9.weight.copy_(torch.from_numpy(prev["fc_9.kernel"].astype(np.float32).T)); head.fc9.bias.copy_(torch.from_numpy(prev["fc_9.bias"].astype(np.float32)))
+            head.fc12.weight.copy_(torch.from_numpy(prev["fc_12.kernel"].astype(np.float32).T)); head.fc12.bias.copy_(torch.from_numpy(prev["fc_12.bias"].astype(np.float32)))
+            for name, m in (("lstm_10", head.l10), ("lstm_10_back", head.l10b), ("lstm_11", head.l11), ("lstm_11_back", head.l11b)):
+                m.weight_ih_l0.copy_(torch.from_numpy(prev[name + ".kernel"].astype(np.float32).T))
+                m.weight_hh_l0.copy_(torch.from_numpy(prev[name + ".recurrent_kernel"].astype(np.float32).T))
+                m.bias_ih_l0.copy_(torch.from_numpy(prev[name + ".bias"].astype(np.float32))); m.bias_hh_l0.zero_()
+        print("warm start from", OUT, flush=True)
     epochs = int(os.environ.get("B2O_TRAIN_EPOCHS", 120))
     opt = torch.optim.Adam(head.parameters(), lr=2e-3, weight_decay=1e-5)
-    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=3e-3, total_steps=epochs * ((len(y_train) + 63) // 64))
+    sched = torch.optim.lr_scheduler.OneCycleLR(opt, max_lr=float(os.environ.get("B2O_TRAIN_LR", 3e-3)), total_steps=epochs * ((len(y_train) + 63) // 64))
     scale = float(x_train.std())
     for ep in range(epochs):
         perm = torch.randperm(len(y_train))
@@ -193,7 +215,7 @@ def main():
     exported = head.export()
     full = dict(crnn_w); full.update({k: v.astype(np.float32) for k, v in exported.items()})
     with torch.no_grad():                                        # the export really is the oracle's network
-        d = np.load(os.path.join(CACHE, "set_%d.npz" % PAGE_SETS[1][0]), allow_pickle=True)
+        d = np.load(os.path.join(CACHE, "set_%d_j%d.npz" % (PAGE_SETS[1][0], JITTER_COPIES)), allow_pickle=True)
         probs = crnn.crnn_logits(full, d["crops"].astype(np.float32) / 255)
         print("oracle texts on set 21:", crnn.labels_to_text(crnn.ctc_greedy(probs)), "labels:", list(d["labels"]))
     os.makedirs(os.path.dirname(OUT), exist_ok=True)
