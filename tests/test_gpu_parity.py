@@ -741,6 +741,12 @@ def test_recognize_records_equals_recognize(cuda_device):
     assert np.array_equal(boxes, np.concatenate([np.stack([b for _, b in g]) for g in ref if g]))
     # the one-process form of the sharded call goes through the same records
     assert [[t for t, _ in g] for g in D.recognize_sharded(pipe, pages, max_boxes=16)] == [[t for t, _ in g] for g in ref]
+    # a record too small for a page is never silent: RecordOverflow names the image; "auto" sizes the records from the counts
+    with pytest.raises(D.RecordOverflow):
+        D.recognize_sharded(pipe, pages, max_boxes=2)
+    auto = D.recognize_sharded(pipe, pages, max_boxes="auto")
+    assert [[t for t, _ in g] for g in auto] == [[t for t, _ in g] for g in ref]
+    assert all(np.array_equal(a, b) for ga, gb in zip(auto, ref) for (_, a), (_, b) in zip(ga, gb))
 
 
 # ------------------------------------------------------------------------------- BASELINE.json sizes: properties
