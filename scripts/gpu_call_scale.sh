@@ -14,7 +14,7 @@ a=json.loads(open("$O/bench_1gpu.json").read().strip().splitlines()[-1])
 for tag in ("${N}gpu","${N}gpu_gather"):
     b=json.loads(open("$O/bench_"+tag+".json").read().strip().splitlines()[-1])
     print(tag, "value", round(b["value"],1), "e2e", round(b["e2e"]["value"],1), "efficiency vs N=1 on this box", round(b["value"]/($N*a["value"]),4),
-          "per-rank ms", b.get("per_rank_ms_per_step"), "decode ms", b.get("rank0_decode_ms_per_step"))
+          "per-rank ms", b.get("per_rank_ms_per_step"), "decode ms", b.get("rank0_decode_ms_per_step"), "words", b.get("words_per_step"), b.get("words_read_correctly"))
 print("1gpu", round(a["value"],1), a["clocks"])
 PY
 tail -n 3 $O/*.err
