@@ -55,10 +55,11 @@ def stn_sample(feat_nhwc, theta):
     144-152), so samples past the last row/column get zero total weight.
     """
     B, Hh, Ww, C = feat_nhwc.shape
-    xs = torch.linspace(-1.0, 1.0, Ww)
-    ys = torch.linspace(-1.0, 1.0, Hh)
+    dev = feat_nhwc.device
+    xs = torch.linspace(-1.0, 1.0, Ww, device=dev)
+    ys = torch.linspace(-1.0, 1.0, Hh, device=dev)
     gy, gx = torch.meshgrid(ys, xs, indexing="ij")
-    grid = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.ones(Hh * Ww)], 0)   # (3, Hh*Ww)
+    grid = torch.stack([gx.reshape(-1), gy.reshape(-1), torch.ones(Hh * Ww, device=dev)], 0)   # (3, Hh*Ww)
     tg = theta.reshape(B, 2, 3) @ grid                                              # (B,2,P)
     x = 0.5 * (tg[:, 0] + 1.0) * float(Ww)
     y = 0.5 * (tg[:, 1] + 1.0) * float(Hh)
