@@ -46,8 +46,8 @@ def workload_config(n_gpus):
         "pages_per_gpu": PAGES_PER_RANK, "global_batch": PAGES_PER_RANK * n_gpus,
         "source": f"{PAGE_H}x{PAGE_W}x3 uint8, {WORDS_PER_PAGE} cv2.putText words/page",
         "detector_input": "1536x1536", "scale": SCALE, "parallelism": f"dp{n_gpus}",
-        "weights": "no pretrained files offline: CRAFT seeded synthetic with textlike routing; CRNN seeded backbone + head fitted "
-                   "on the rendered pages (oracle/train_crnn_head.py) -- the words found are the rendered words",
+        "weights": "no pretrained files offline: CRAFT seeded synthetic with textlike routing; CRNN = the reference architecture "
+                   "trained on rendered Hershey-font words (oracle/train_crnn_full.py) -- the words found are the rendered words",
         "l2": "per-step activations (>40 GB) exceed the 126 MB L2; no explicit flush needed",
     }
 
@@ -310,8 +310,7 @@ def run_b200(args):
         if world > 1:
             dist.destroy_process_group()
         return 0
-    # what the benchmarked step produced, checked at full size on rank 0's pages (outside the timed region; the recognizer
-    # head is fitted on exactly these pages -- the other ranks' pages are only ever counted)
+    # what the benchmarked step produced, checked at full size on rank 0's pages (outside the timed region)
     hit, rendered = words_read(pipe.recognize(pages_dev), page_words, page_rects)
     total_pages = PAGES_PER_RANK * world
     value = total_pages * args.steps / (ms_dev / 1e3)

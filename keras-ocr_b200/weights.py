@@ -143,8 +143,7 @@ def synthetic_craft_weights(seed=0, textlike=False):
     return w
 
 
-HERSHEY_HEAD = "crnn_hershey_head.npz"      # keras-ocr_b200/data/: fc_9 + BiLSTM + fc_12 fitted on rendered words (see below)
-HERSHEY_SEED = 2                            # the backbone seed that head was fitted on
+HERSHEY = "crnn_hershey.npz"                # keras-ocr_b200/data/: the reference CRNN trained on rendered words (see below)
 
 
 def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False, stn=True, color=False):
@@ -152,22 +151,18 @@ def synthetic_crnn_weights(seed=1, alphabet=ALPHABET, decisive=False, stn=True, 
 
     ``color=True``: ``conv_1`` takes 3 input channels (``build_model(color=True)``, recognition.py:214).
     ``stn=False``: no spatial-transformer tensors (the ``build_model(stn=False)`` variant, recognition.py:196, 243).
-    ``decisive=True`` (seed 2, default alphabet only): the convolutional backbone and the spatial transformer keep their
-    seeded random weights, and everything after the transformer -- ``fc_9``, the four LSTMs, ``fc_12`` -- comes from
-    ``data/crnn_hershey_head.npz``, fitted with CTC loss on the crops the oracle pipeline cuts out of
-    ``oracle.synth.text_images`` pages (``oracle/train_crnn_head.py``; cv2's Hershey font, no pretrained file involved).
-    That recognizer READS the synthetic pages: its per-step argmax is decided by a wide margin, so decoded strings can be
-    compared for identity (BASELINE.json north_star) instead of up to the near-ties random weights leave."""
+    ``decisive=True`` (default alphabet, gray, with STN; ``seed`` is ignored): every tensor comes from
+    ``data/crnn_hershey.npz`` -- the reference architecture TRAINED with CTC loss on words rendered in cv2's Hershey font
+    and cut out as the oracle pipeline cuts them (``oracle/train_crnn_full.py``; 3.5 minutes on one B200; no pretrained file
+    involved).  It reads the synthetic pages (99.7 % of unseen synthetic crops, 100 % of the crops of pages it never saw), its
+    per-step argmax is decided by a wide margin and its strings do not change when a box moves by a pixel, so decoded
+    strings can be compared for identity (BASELINE.json north_star) instead of up to the near-ties random weights leave."""
     if decisive:
         import os
-        assert seed == HERSHEY_SEED and alphabet == ALPHABET, "the fitted head belongs to seed 2 / the default alphabet"
-        w = synthetic_crnn_weights(seed, alphabet)
-        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", HERSHEY_HEAD)
-        with np.load(path) as head:
-            for k in head.files:
-                assert k in w and w[k].shape == head[k].shape, k
-                w[k] = head[k].astype(np.float32)
-        return w
+        assert alphabet == ALPHABET and stn and not color, "the trained recognizer is the default architecture / alphabet"
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", HERSHEY)
+        with np.load(path) as data:
+            return {k: data[k].astype(np.float32) for k in data.files}
     rng = np.random.default_rng(seed)
     w = {}
     for name, cin, cout, k, bn in CRNN_CONVS:

@@ -18,7 +18,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 from oracle import crnn                                         # noqa: E402
-from oracle.train_crnn_head import labelled_crops               # noqa: E402
+from oracle.word_crops import labelled_crops               # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "c3_crops.npz")
 

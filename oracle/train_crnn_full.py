@@ -1,8 +1,8 @@
 """Train the whole CRNN recognizer on rendered words -- TEST INFRASTRUCTURE, meant to run where torch has a GPU
 (``gpurun -- python -m oracle.train_crnn_full``; a few minutes on one B200, PyTorch/cuDNN doing the training arithmetic).
 
-``oracle/train_crnn_head.py`` fits only the head on frozen random features: that fixture memorises its pages and is brittle to
-a box that moves by a pixel.  This script trains every layer of the reference architecture (``build_model``,
+(An earlier fixture fitted only the head on frozen random features: it memorised its pages and its strings changed when a
+box moved by a pixel.)  This script trains every layer of the reference architecture (``build_model``,
 recognition.py:187-350, restated with torch.nn modules in exactly ``oracle/crnn.py``'s arithmetic -- the export is checked
 against ``oracle.crnn.crnn_logits``) with CTC loss on
 
@@ -10,8 +10,8 @@ against ``oracle.crnn.crnn_logits``) with CTC loss on
   font, thickness 2, anti-aliased, dark colour on white), up-scaled 2x like ``tools.resize_image``, converted to gray and cut
   out by ``imageops.warp_box`` from a box with the margins the oracle detector leaves around a word (statistics measured
   on oracle-pipeline boxes: 0.30 / 0.26 / 0.40 / 0.23 of the glyph height left / right / top / bottom) plus jitter;
-* the real crops the ORACLE pipeline cuts out of the test / bench pages (``oracle/_train_data/real_crops.npz``, packed from
-  ``train_crnn_head``'s cache), including box-jittered copies.
+* the real crops the ORACLE pipeline cuts out of the test / bench pages (``oracle/_train_data/real_crops.npz``, written by
+  ``python -m oracle.word_crops``), including box-jittered copies; four pages are held out to measure generalisation.
 
 The result is a small model that actually READS the Hershey font: it generalises to pages it has not seen, and its strings
 do not change when a box moves by a pixel -- which is what lets the chained parity test assert every string.
