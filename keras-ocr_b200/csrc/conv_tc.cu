@@ -420,7 +420,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
   float* const tail_s = aff + 4 * p.cout;
   if (BLOCK_N == 16 && p.tail_out != nullptr) {
     for (int i = threadIdx.x; i < TAIL_FLOATS; i += NUM_THREADS)
-      tail_s[i] = i < 256 ? p.tail_w6[i] : (i < 272 ? p.tail_b6[i - 256] : (i < 304 ? p.tail_w8[i - 272] : p.tail_b8[i - 304]));
+      // w6 is staged TRANSPOSED ([out j][in c]): a thread's 16 weights of one output are contiguous -> four LDS.128
+      tail_s[i] = i < 256 ? p.tail_w6[(i & 15) * 16 + (i >> 4)] : (i < 272 ? p.tail_b6[i - 256] : (i < 304 ? p.tail_w8[i - 272] : p.tail_b8[i - 304]));
   }
   const float* const e_s1 = p.aff_smem ? aff : p.s1;
   const float* const e_t1 = p.aff_smem ? aff + p.cout : p.t1;
@@ -770,7 +771,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
           for (int j = 0; j < 16; ++j) {
             float a = tail_s[256 + j];
 #pragma unroll
-            for (int c = 0; c < 16; ++c) a = fmaf(x[c], tail_s[c * 16 + j], a);
+            for (int c4 = 0; c4 < 16; c4 += 4) {
+              const float4 wv = *reinterpret_cast<const float4*>(tail_s + j * 16 + c4);
+              a = fmaf(x[c4], wv.x, a); a = fmaf(x[c4 + 1], wv.y, a); a = fmaf(x[c4 + 2], wv.z, a); a = fmaf(x[c4 + 3], wv.w, a);
+            }
             a = fmaxf(a, 0.0f);
             o0 = fmaf(a, tail_s[272 + j * 2 + 0], o0);
             o1 = fmaf(a, tail_s[272 + j * 2 + 1], o1);
