@@ -65,6 +65,7 @@ int build_layer(b2o_ctx* ctx, ConvLayer& L, const std::string& name, int cin, in
           for (int o = 0; o < cout; ++o)
             wf[(static_cast<size_t>(ky * ksize + kx) * cin + c) * cout + o] = wget(o, c, ky, kx);
     if (!(L.w_f32 = dev_upload(ctx, wf))) return B2O_ERR_CUDA;
+    L.h_w_f32 = wf;
   } else {
     std::vector<__half> wk(static_cast<size_t>(cout) * taps * cin);
     std::vector<float> ws(static_cast<size_t>(taps) * cin * cout);
@@ -79,9 +80,12 @@ int build_layer(b2o_ctx* ctx, ConvLayer& L, const std::string& name, int cin, in
           }
     if (!(L.w_kmajor = dev_upload(ctx, wk))) return B2O_ERR_CUDA;
     if (!(L.w_simt = dev_upload(ctx, ws))) return B2O_ERR_CUDA;
+    if (ws.size() <= 1024) L.h_w_simt = ws;
   }
   if (!(L.s1 = dev_upload(ctx, s1))) return B2O_ERR_CUDA;
   if (!(L.t1 = dev_upload(ctx, t1))) return B2O_ERR_CUDA;
+  L.h_s1 = s1; L.h_t1 = t1;
+  if (s2) { L.h_s2 = *s2; L.h_t2 = *t2; }
   if (s2) {
     if (!(L.s2 = dev_upload(ctx, *s2))) return B2O_ERR_CUDA;
     if (!(L.t2 = dev_upload(ctx, *t2))) return B2O_ERR_CUDA;
@@ -243,6 +247,7 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   if (const char* e = getenv("B2O_TC_BOX16")) { const int v = atoi(e); ctx->tc_box16 = v == 0 ? 0 : (v == 10 ? 10 : 16); ctx->tc_box_forced = v != 0; }
   if (const char* e = getenv("B2O_TC_BOX_ALL")) ctx->tc_box_all = atoi(e) != 0;
   if (const char* e = getenv("B2O_UPCONV_COMMUTE")) ctx->no_commute = atoi(e) == 0;      // 1: commuted decoder upsampling (opt-in, see common.cuh)
+  if (const char* e = getenv("B2O_TC_AFF")) ctx->tc_aff_const = std::string(e) != "smem";
   if (const char* e = getenv("B2O_FUSED_TAIL")) ctx->no_fused_tail = atoi(e) == 0;      // 0: separate head_tail_kernel (A/B, tests)
   if (const char* e = getenv("B2O_TC_PAIR")) {        // default 1; 0 = single-CTA tiles (A/B runs); 2 = generic tiles too
     ctx->tc_pair = atoi(e) != 0;
@@ -580,7 +585,11 @@ extern "C" int b2o_craft_forward(b2o_ctx* ctx, const uint8_t* img, int n, int h,
   if (ctx->conv_engine == B2O_CONV_AUTO && L("conv_cls.4").block_n == 16 && !ctx->no_fused_tail) {
     // conv_cls.6 + conv_cls.8 ride in conv_cls.4's epilogue (same arithmetic as head_tail_kernel, bit for bit):
     // one launch and the 16-channel map's round trip through HBM less
-    const ConvTail tail = {L("conv_cls.6").w_simt, L("conv_cls.6").t1, L("conv_cls.8").w_simt, L("conv_cls.8").t1, scores};
+    const ConvLayer &L6 = L("conv_cls.6"), &L8 = L("conv_cls.8");
+    ConvTail tail = {L6.w_simt, L6.t1, L8.w_simt, L8.t1, scores};
+    if (L6.h_w_simt.size() == 256 && L8.h_w_simt.size() == 32) {
+      tail.h_w6 = L6.h_w_simt.data(); tail.h_b6 = L6.h_t1.data(); tail.h_w8 = L8.h_w_simt.data(); tail.h_b8 = L8.h_t1.data();
+    }
     B2O_RETURN_IF(conv_tc_run(ctx, L("conv_cls.4"), h2, h3, 0, st, nullptr, 1, &tail));
   } else {
     B2O_RETURN_IF(conv_run(ctx, L("conv_cls.4"), h2, h3, 0, st));

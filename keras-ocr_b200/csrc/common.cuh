@@ -66,6 +66,9 @@ struct ConvLayer {
   float* w_simt = nullptr;     // [taps][cin][cout] fp32 holding the fp16-rounded values (SIMT engine)
   float* w_f32 = nullptr;      // [taps][cin][cout] fp32 (only for the 3-channel / 1-channel stems)
   float *s1 = nullptr, *t1 = nullptr, *s2 = nullptr, *t2 = nullptr;
+  std::vector<float> h_w_f32;                  // host copy of w_f32 (the 1- / 3-channel CRNN stem: kernel-parameter filter bank)
+  std::vector<float> h_w_simt;                 // host copy of w_simt for layers of <= 1024 weights (fused into other kernels' parameters)
+  std::vector<float> h_s1, h_t1, h_s2, h_t2;   // host copies: passed to the tensor-core kernel as a kernel parameter (constant bank)
   CUtensorMap wmap;            // TMA map over w_kmajor (box 64 x block_n)
   CUtensorMap wmap_pair;       // the same with box 64 x block_n/2: one CTA's half of a B tile (cta_group::2)
   bool pair_ok = false;        // wmap_pair is valid (64-channel chunks, block_n >= 64)
@@ -96,6 +99,7 @@ struct b2o_ctx {
   // upsample-add in the full-resolution layer's epilogue).  Numerically validated, but measured SLOWER on B200
   // (profiles/r2e_layers.csv: upconv4.0 1.39 + upsample 0.85 ms -> 0.21 + 2.32 ms): the epilogue's per-pixel 16-byte
   // gathers of the four taps are LSU-wavefront-bound.  Default: explicit UpsampleLike kernels.
+  bool tc_aff_const = true;    // epilogue constants as a kernel parameter (constant cache); B2O_TC_AFF=smem: round-1 staging in shared memory / global loads
   bool no_commute = true;
   bool no_fused_tail = false;  // B2O_FUSED_TAIL=0: conv_cls.6/.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue
   std::set<const void*> configured;   // kernels whose per-device launch attributes are set on this device
@@ -126,8 +130,9 @@ void jpeg_release(b2o_ctx* ctx);
 // CRAFT tail fused into the epilogue of a 16-channel tensor-core layer: conv_cls.6 (1x1 16->16, ReLU) and conv_cls.8
 // (1x1 16->2) on the 16 channels a thread already holds; fp32 (text, link) scores out (detection.py:404-410).
 struct ConvTail {
-  const float *w6, *b6, *w8, *b8;   // [cin 16][cout 16] fp32 (fp16-rounded values), [16], [16][2], [2]
+  const float *w6, *b6, *w8, *b8;   // [cin 16][cout 16] fp32 (fp16-rounded values), [16], [16][2], [2] -- device
   float* scores;                    // (n,h,w,2)
+  const float *h_w6 = nullptr, *h_b6 = nullptr, *h_w8 = nullptr, *h_b8 = nullptr;   // the same on the host (kernel-parameter path)
 };
 
 // ---- engines (conv_tc.cu, conv_simt.cu) -------------------------------------------------------

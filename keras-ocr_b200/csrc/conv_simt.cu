@@ -6,6 +6,8 @@
 //   * stem_crnn_kernel : CRNN conv_1 (1->64, recognition.py:217-219)
 //   * maxpool2 / maxpool3s1 / upsample (MaxPooling2D detection.py:100-102,365-367; UpsampleLike 290-309)
 //   * head_tail_kernel : conv_cls.6 (1x1 16->16 ReLU) + conv_cls.8 (1x1 16->2) fused, fp32 scores
+#include <string.h>
+
 #include "common.cuh"
 
 namespace {
@@ -175,6 +177,8 @@ __global__ void normalize16_kernel(const uint8_t* __restrict__ img, long long to
 
 // CRNN conv_1: x (B,200,31[,CIN]) fp16 -> (B,200,31,64) fp16, 3x3 same, bias + ReLU.  CIN = 1 (gray, the default) or 3
 // (build_model(color=True), recognition.py:214).  Weights [tap][cin][64].
+// (The 576 filter taps stay in shared memory: read as a kernel parameter through the constant cache -- 576 scalar LDC per
+// thread -- the kernel took 1.57 ms instead of 0.36, gpurun call r2k; the constant bank only pays for a few dozen reads.)
 template <int CIN>
 __global__ void __launch_bounds__(128)
 stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt /*[9*CIN][64]*/,

@@ -61,7 +61,8 @@ struct TcParams {
   int na, nb;                             // ring depths
   int a_stride, a_bytes;                  // bytes between A stages / bytes one A box delivers
   int off_b, off_bar;                     // shared-memory offsets
-  int aff_smem;                           // epilogue constants staged in shared memory behind the barriers
+  int aff_smem;                           // epilogue constants staged in shared memory behind the barriers (B2O_TC_AFF=smem)
+  int aff_const;                          // epilogue constants read from the AffConst kernel parameter (default)
   int group;                              // MODE 3: A stages per tile (p.na then counts groups)
   int issuers;                            // active MMA-issuing warps (2 = alternate tiles)
   const float *s1, *t1, *s2, *t2;
@@ -305,6 +306,30 @@ struct TileIter {
   }
 };
 
+// Per-channel epilogue constants as a KERNEL PARAMETER (constant bank): an epilogue warp reads them with a warp-uniform
+// index, which the constant cache serves without touching the L1TEX data pipe.  Staged in shared memory (round 1) the
+// same reads were 392 M LDS wavefronts per stem launch and 592 M per conv2 launch -- l1tex__data_pipe_lsu_wavefronts at
+// 98 % / 90 % of peak, on the very pipe the tensor core fetches its shared-memory operands through
+// (profiles/r2final_conv_full.csv).  16 KB of parameters need CUDA >= 12.1 (large kernel parameters).
+constexpr int AFF_MAX = 1024;
+struct AffConst {
+  float s1[AFF_MAX], t1[AFF_MAX], s2[AFF_MAX], t2[AFF_MAX];
+  float tail[320];          // fused CRAFT tail: [w6 transposed [out j][in c] 256 | b6 16 | w8 [j][2] 32 | b8 2]
+};
+
+__device__ __forceinline__ void epi_affine_c(const TcParams& p, const AffConst& ac, const uint32_t* v, int c0, float* y) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) y[j] = fmaf(__uint_as_float(v[j]), ac.s1[c0 + j], ac.t1[c0 + j]);
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.0f);
+  }
+  if (p.s2 != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = fmaf(y[j], ac.s2[c0 + j], ac.t2[c0 + j]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------ kernel
 // Epilogue arithmetic of one 16-column accumulator chunk: y = relu?(acc * s1 + t1) [* s2 + t2].
 __device__ __forceinline__ void epi_affine(const TcParams& p, const float* s1, const float* t1, const float* s2,
@@ -367,7 +392,7 @@ __device__ __forceinline__ void epi_pool8(uint32_t* pk) {
 template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false, bool UPADD = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap,
-               const TcParams p) {
+               const TcParams p, const __grid_constant__ AffConst ac) {
   static_assert(!BOX16 || MODE == 3, "the single-box tile is implemented for grouped tiles (whole tile on one barrier)");
   constexpr int B_ROWS = PAIR ? BLOCK_N / 2 : BLOCK_N;     // filter rows staged by one CTA
   constexpr int B_BYTES = B_ROWS * KCH * 2;
@@ -759,25 +784,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap amap, const __grid_constant__
           }
         }
         float y[CH];
-        epi_affine(p, e_s1, e_t1, e_s2, e_t2, v, c0, y);
+        if (p.aff_const) epi_affine_c(p, ac, v, c0, y);     // warp-uniform
+        else epi_affine(p, e_s1, e_t1, e_s2, e_t2, v, c0, y);
         if (BLOCK_N == 16 && p.tail_out != nullptr) {        // warp-uniform; only the 16-channel instances carry it
           // The unfused path stores these 16 channels as fp16 and head_tail_kernel reads them back: round the same way
           // and run the same fmaf chains, so the scores are bit-identical to conv_cls.4 -> head_tail_kernel.
           float x[CH];
 #pragma unroll
           for (int j = 0; j < CH; ++j) x[j] = __half2float(__float2half_rn(y[j]));
-          float o0 = tail_s[304], o1 = tail_s[305];
+          float o0, o1;
+          if (p.aff_const) {                                   // weights from the constant bank (no shared-memory pipe traffic)
+            o0 = ac.tail[304]; o1 = ac.tail[305];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float a = tail_s[256 + j];
+            for (int j = 0; j < 16; ++j) {
+              float a = ac.tail[256 + j];
 #pragma unroll
-            for (int c4 = 0; c4 < 16; c4 += 4) {
-              const float4 wv = *reinterpret_cast<const float4*>(tail_s + j * 16 + c4);
-              a = fmaf(x[c4], wv.x, a); a = fmaf(x[c4 + 1], wv.y, a); a = fmaf(x[c4 + 2], wv.z, a); a = fmaf(x[c4 + 3], wv.w, a);
+              for (int c = 0; c < 16; ++c) a = fmaf(x[c], ac.tail[j * 16 + c], a);
+              a = fmaxf(a, 0.0f);
+              o0 = fmaf(a, ac.tail[272 + j * 2 + 0], o0);
+              o1 = fmaf(a, ac.tail[272 + j * 2 + 1], o1);
             }
-            a = fmaxf(a, 0.0f);
-            o0 = fmaf(a, tail_s[272 + j * 2 + 0], o0);
-            o1 = fmaf(a, tail_s[272 + j * 2 + 1], o1);
+          } else {
+            o0 = tail_s[304]; o1 = tail_s[305];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float a = tail_s[256 + j];
+#pragma unroll
+              for (int c4 = 0; c4 < 16; c4 += 4) {
+                const float4 wv = *reinterpret_cast<const float4*>(tail_s + j * 16 + c4);
+                a = fmaf(x[c4], wv.x, a); a = fmaf(x[c4 + 1], wv.y, a); a = fmaf(x[c4 + 2], wv.z, a); a = fmaf(x[c4 + 3], wv.w, a);
+              }
+              a = fmaxf(a, 0.0f);
+              o0 = fmaf(a, tail_s[272 + j * 2 + 0], o0);
+              o1 = fmaf(a, tail_s[272 + j * 2 + 1], o1);
+            }
           }
           if (valid) reinterpret_cast<float2*>(p.tail_out)[pix] = make_float2(o0, o1);
           return;
@@ -921,9 +961,19 @@ double pick_box(int N, int H, int W, int* bw_l, int* bh_l, int* bn_l) {
 
 constexpr int kRetrySingle = 1;            // launch(): the pair launch was refused, plan the layer again without pairs
 
+thread_local const float* g_tail_host = nullptr;     // the fused tail's constants in AffConst::tail order (set by conv_tc_run)
+
 template <int BLOCK_N, int KCH, int MODE, bool PAIR, bool BOX16 = false, bool UPADD = false>
 int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcParams& p, int smem_bytes,
            cudaStream_t st) {
+  static thread_local AffConst ac;                         // 16 KB: filled per launch from the layer's host copies
+  if (p.aff_const) {
+    const size_t nb = static_cast<size_t>(L.cout) * sizeof(float);
+    memcpy(ac.s1, L.h_s1.data(), nb);
+    memcpy(ac.t1, L.h_t1.data(), nb);
+    if (!L.h_s2.empty()) { memcpy(ac.s2, L.h_s2.data(), nb); memcpy(ac.t2, L.h_t2.data(), nb); }
+    if (p.tail_out != nullptr && g_tail_host != nullptr) memcpy(ac.tail, g_tail_host, TAIL_FLOATS * sizeof(float));
+  }
   const void* fn = reinterpret_cast<const void*>(&conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD>);
   if (!ctx->configured.count(fn)) {                        // a per-device attribute: remembered per context
     B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD>,
@@ -951,7 +1001,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
     attr.val.clusterDim.x = 2; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
     cfg.attrs = &attr;
     cfg.numAttrs = 1;
-    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD>, amap, L.wmap_pair, p);
+    const cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD>, amap, L.wmap_pair, p, ac);
     if (le != cudaSuccess) {
       // a device / partition that cannot co-schedule two such CTAs on a TPC: fall back, once and for good, to the
       // single-CTA tiles of the same kernel (bit-identical results)
@@ -962,7 +1012,7 @@ int launch(b2o_ctx* ctx, const CUtensorMap& amap, const ConvLayer& L, const TcPa
       return kRetrySingle;
     }
   } else {
-    conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p);
+    conv_tc_kernel<BLOCK_N, KCH, MODE, PAIR, BOX16, UPADD><<<grid, NUM_THREADS, smem_bytes, st>>>(amap, L.wmap, p, ac);
   }
   B2O_LAUNCH_CHECK(ctx);
   if (ctx->profile) {
@@ -1083,7 +1133,11 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
   p.issuers = 1;
   // layers with few output channels keep their epilogue constants (s1,t1,s2,t2) in shared memory: their
   // epilogue is latency-bound and the per-chunk __ldg's of the constants were its top stall (ncu source view)
-  p.aff_smem = L.cout <= 256 ? 1 : 0;
+  // measured per layer (profiles/r2l_epilogue_constants_ab.txt): wins wherever the constants used to be staged in shared
+  // memory (cout <= 256: stem 3.15 -> 2.88 ms, slice1.7 2.08 -> 1.92, conv_cls.4 + tail 0.90 -> 0.64), loses 1-2 % against
+  // the plain global loads of the wider layers -- those keep them
+  p.aff_const = (ctx->tc_aff_const && L.cout <= 256 && static_cast<int>(L.h_s1.size()) == L.cout) ? 1 : 0;
+  p.aff_smem = (!p.aff_const && L.cout <= 256) ? 1 : 0;
   const int aff_bytes = (p.aff_smem ? 4 * L.cout * 4 : 0) + (tail ? TAIL_FLOATS * 4 : 0);
   const int budget = SMEM_TOTAL - 1024 /*alignment slack*/ - 512 /*barriers*/ - aff_bytes;
   p.a_bytes = p.halo ? 18 * 8 * kch * 2 : 128 * kch * 2;
@@ -1146,6 +1200,16 @@ int conv_tc_run(b2o_ctx* ctx, const ConvLayer& L, const TensorView& in, const Te
 #endif
   p.s1 = L.s1; p.t1 = L.t1; p.s2 = L.s2; p.t2 = L.t2; p.relu = L.relu;
   if (up_add) { p.up_src = up_add->ptr; p.up_ld = up_add->ld; p.UH = up_add->h; p.UW = up_add->w; }
+  float tail_host[TAIL_FLOATS];
+  g_tail_host = nullptr;
+  if (tail && tail->h_w6 != nullptr) {                      // [w6 transposed | b6 | w8 | b8]
+    for (int j = 0; j < 16; ++j)
+      for (int c = 0; c < 16; ++c) tail_host[j * 16 + c] = tail->h_w6[c * 16 + j];
+    memcpy(tail_host + 256, tail->h_b6, 16 * sizeof(float));
+    memcpy(tail_host + 272, tail->h_w8, 32 * sizeof(float));
+    memcpy(tail_host + 304, tail->h_b8, 2 * sizeof(float));
+    g_tail_host = tail_host;
+  }
   if (tail) { p.tail_w6 = tail->w6; p.tail_b6 = tail->b6; p.tail_w8 = tail->w8; p.tail_b8 = tail->b8; p.tail_out = tail->scores; }
   p.out = out.ptr; p.out_ld = out.ld; p.out_f32 = out_f32; p.write_full = write_full;
   if (want_pool) {

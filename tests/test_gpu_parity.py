@@ -856,14 +856,17 @@ def test_decoder_commute_matches_explicit_upsample(cuda_device, monkeypatch, gol
 
 
 @pytest.mark.parametrize("switch", [("B2O_TC_BOX16", "0"), ("B2O_TC_BOX16", "10"), ("B2O_TC_BOX16", "16"), ("B2O_TC_BOX_ALL", "1"), ("B2O_TC_PAIR", "2"),
-                                    ("B2O_FUSED_TAIL", "0")],
-                         ids=["three_boxes_vs_single_box", "box_width_10", "box_width_16", "single_box_everywhere", "generic_pairs", "separate_head_tail"])
+                                    ("B2O_FUSED_TAIL", "0"), ("B2O_TC_AFF", "smem")],
+                         ids=["three_boxes_vs_single_box", "box_width_10", "box_width_16", "single_box_everywhere", "generic_pairs", "separate_head_tail",
+                              "epilogue_constants_in_smem"])
 def test_conv_variants_are_bit_identical(cuda_device, monkeypatch, switch):
     """Kernel variants that keep the MMA / fmaf order of the default path must not change a bit of the CRAFT score
     maps or the CRNN logits:  B2O_TC_BOX16=0 -- three 8 x 18 A boxes per K chunk instead of the default single
     box (dx taps through the descriptor start address), =10 / =16 -- the width of that box (image rows then start inside
     a swizzle atom), B2O_TC_BOX_ALL=1 -- single boxes in every grouped layer;  B2O_TC_PAIR=2 -- CTA pairs on the generic tiles too;
-    B2O_FUSED_TAIL=0 -- conv_cls.6 / conv_cls.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue.
+    B2O_FUSED_TAIL=0 -- conv_cls.6 / conv_cls.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue;
+    B2O_TC_AFF=smem -- the per-channel epilogue constants staged in shared memory / read from global memory (round 1)
+    instead of the kernel-parameter constant bank.
     Sizes: odd tile columns (200 / 8 = 25), several tiles per CTA, and the 768 x 768 case of BASELINE configs[1]."""
     from keras_ocr_b200.detection import Detector
     from keras_ocr_b200.recognition import Recognizer
