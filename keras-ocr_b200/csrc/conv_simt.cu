@@ -179,7 +179,9 @@ __global__ void normalize16_kernel(const uint8_t* __restrict__ img, long long to
 // (build_model(color=True), recognition.py:214).  Weights [tap][cin][64].
 // (The 576 filter taps stay in shared memory: read as a kernel parameter through the constant cache -- 576 scalar LDC per
 // thread -- the kernel took 1.57 ms instead of 0.36, gpurun call r2k; the constant bank only pays for a few dozen reads.)
-template <int CIN>
+// Each thread computes PIX consecutive pixels, so one shared-memory read of a filter tap feeds PIX FMAs (the kernel is
+// bound by the L1TEX data pipe: 97 % with one pixel per thread).
+template <int CIN, int PIX>
 __global__ void __launch_bounds__(128)
 stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float* __restrict__ wgt /*[9*CIN][64]*/,
                  const float* __restrict__ t1, __half* __restrict__ out, int out_ld) {
@@ -190,41 +192,55 @@ stem_crnn_kernel(const __half* __restrict__ x, int B, int H, int W, const float*
   if (threadIdx.x < 64) sb[threadIdx.x] = t1[threadIdx.x];
   __syncthreads();
   const long long total = static_cast<long long>(B) * H * W;
-  const long long pix = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (pix >= total) return;
-  const int w = static_cast<int>(pix % W);
-  const int h = static_cast<int>((pix / W) % H);
-  const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
-  float v[K];
+  const long long pix0 = (static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x) * PIX;
+  if (pix0 >= total) return;
+  float v[PIX][K];
 #pragma unroll
-  for (int ky = 0; ky < 3; ++ky)
+  for (int q = 0; q < PIX; ++q) {
+    const long long pix = pix0 + q < total ? pix0 + q : total - 1;      // a tail thread recomputes the last pixel (not stored)
+    const int w = static_cast<int>(pix % W);
+    const int h = static_cast<int>((pix / W) % H);
+    const int n = static_cast<int>(pix / (static_cast<long long>(W) * H));
 #pragma unroll
-    for (int kx = 0; kx < 3; ++kx) {
-      const int ih = h + ky - 1, iw = w + kx - 1;
-      const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+    for (int ky = 0; ky < 3; ++ky)
 #pragma unroll
-      for (int c = 0; c < CIN; ++c)
-        v[(ky * 3 + kx) * CIN + c] = ok ? __half2float(x[((static_cast<size_t>(n) * H + ih) * W + iw) * CIN + c]) : 0.0f;
-    }
-  __half* o = out + static_cast<size_t>(pix) * out_ld;
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ih = h + ky - 1, iw = w + kx - 1;
+        const bool ok = ih >= 0 && ih < H && iw >= 0 && iw < W;
+#pragma unroll
+        for (int c = 0; c < CIN; ++c)
+          v[q][(ky * 3 + kx) * CIN + c] = ok ? __half2float(x[((static_cast<size_t>(n) * H + ih) * W + iw) * CIN + c]) : 0.0f;
+      }
+  }
 #pragma unroll 1
   for (int cb = 0; cb < 64; cb += 16) {                    // 16 channels = one 32-byte sector per 256-bit store
-    float acc[16];
+    float acc[PIX][16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) acc[j] = sb[cb + j];
+    for (int q = 0; q < PIX; ++q)
+#pragma unroll
+      for (int j = 0; j < 16; ++j) acc[q][j] = sb[cb + j];
 #pragma unroll
     for (int k = 0; k < K; ++k)
 #pragma unroll
-      for (int j = 0; j < 16; ++j) acc[j] = fmaf(v[k], sw[k * 64 + cb + j], acc[j]);
-    uint32_t pk[8];
+      for (int j = 0; j < 16; ++j) {
+        const float wv = sw[k * 64 + cb + j];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const __half2 h = __floats2half2_rn(fmaxf(acc[2 * j], 0.f), fmaxf(acc[2 * j + 1], 0.f));
-      pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+        for (int q = 0; q < PIX; ++q) acc[q][j] = fmaf(v[q][k], wv, acc[q][j]);
+      }
+#pragma unroll
+    for (int q = 0; q < PIX; ++q) {
+      if (pix0 + q >= total) break;
+      uint32_t pk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const __half2 h = __floats2half2_rn(fmaxf(acc[q][2 * j], 0.f), fmaxf(acc[q][2 * j + 1], 0.f));
+        pk[j] = *reinterpret_cast<const uint32_t*>(&h);
+      }
+      __half* o = out + static_cast<size_t>(pix0 + q) * out_ld;
+      asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + cb), "r"(pk[0]), "r"(pk[1]),
+                   "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
+                   : "memory");
     }
-    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(o + cb), "r"(pk[0]), "r"(pk[1]),
-                 "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7])
-                 : "memory");
   }
 }
 
@@ -471,8 +487,8 @@ int normalize16_run(b2o_ctx* ctx, const uint8_t* img, int n, int h, int w, __hal
 
 int stem_crnn_run(b2o_ctx* ctx, const ConvLayer& L, const __half* x, int b, const TensorView& out, cudaStream_t st) {
   const long long total = static_cast<long long>(b) * out.h * out.w;
-  if (L.cin == 3) stem_crnn_kernel<3><<<blocks_for(total, 128), 128, 0, st>>>(x, b, out.h, out.w, L.w_f32, L.t1, out.ptr, out.ld);
-  else stem_crnn_kernel<1><<<blocks_for(total, 128), 128, 0, st>>>(x, b, out.h, out.w, L.w_f32, L.t1, out.ptr, out.ld);
+  if (L.cin == 3) stem_crnn_kernel<3, 2><<<blocks_for((total + 1) / 2, 128), 128, 0, st>>>(x, b, out.h, out.w, L.w_f32, L.t1, out.ptr, out.ld);
+  else stem_crnn_kernel<1, 4><<<blocks_for((total + 3) / 4, 128), 128, 0, st>>>(x, b, out.h, out.w, L.w_f32, L.t1, out.ptr, out.ld);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }
