@@ -228,43 +228,49 @@ def rectify_boxes(boxes, tolerance=1e-3):
 
 
 # ----------------------------------------------------------------------------------- drawing (host, cv2)
+def _plain_boxes(boxes, boxes_format):
+    """The (4,2) corner arrays inside any of the three box containers the reference passes around."""
+    if boxes_format == "lines":
+        return [quad for line in boxes for quad, _character in line]
+    if boxes_format == "predictions":
+        return [quad for _word, quad in boxes]
+    return list(boxes)
+
+
 def drawBoxes(image, boxes, color=(255, 0, 0), thickness=5, boxes_format="boxes"):
-    """tools.drawBoxes (reference tools.py:189-229): polylines of ``boxes`` on a copy of ``image``; ``boxes_format`` is
-    "boxes" ((N,4,2) array as from ``Detector.detect``), "lines" (lists of (box, character)) or "predictions"
-    ((word, box) tuples as from ``Pipeline.recognize``)."""
+    """tools.drawBoxes (reference tools.py:189-229): the outlines of ``boxes`` on a copy of ``image``.  ``boxes_format``:
+    "boxes" = (N,4,2) array as from ``Detector.detect``; "lines" = lists of (box, character); "predictions" = (word, box)
+    tuples as from ``Pipeline.recognize``.  An empty container returns the image itself, as upstream."""
     import cv2
 
     if len(boxes) == 0:
         return image
     canvas = image.copy()
-    if boxes_format == "lines":
-        boxes = [box for line in boxes for box, _ in line]
-    if boxes_format == "predictions":
-        boxes = [box for _, box in boxes]
-    for box in boxes:
-        cv2.polylines(img=canvas, pts=box[np.newaxis].astype("int32"), color=color, thickness=thickness, isClosed=True)
+    for quad in _plain_boxes(boxes, boxes_format):
+        cv2.polylines(canvas, np.asarray(quad)[np.newaxis].astype("int32"), True, color, thickness)
     return canvas
 
 
 def drawAnnotations(image, predictions, ax=None):
-    """tools.drawAnnotations (reference tools.py:150-186): boxes plus the recognised words as margin annotations on a
-    matplotlib axis.  matplotlib is an optional dependency here as it is upstream."""
+    """tools.drawAnnotations (reference tools.py:150-186): the boxes on the image plus every recognised word in the
+    margin -- words whose box starts in the left half on the left, the others on the right, each column top to bottom
+    in the order of the boxes' upper edges, joined to its box by a red arrow.  Needs matplotlib, like upstream."""
     import matplotlib.pyplot as plt
 
     if ax is None:
-        _, ax = plt.subplots()
-    ax.imshow(drawBoxes(image=image, boxes=predictions, boxes_format="predictions"))
-    predictions = sorted(predictions, key=lambda p: p[1][:, 1].min())
-    left = [(w, b) for w, b in predictions if b[:, 0].min() < image.shape[1] / 2]
-    right = [(w, b) for w, b in predictions if not b[:, 0].min() < image.shape[1] / 2]
-    ax.set_yticks([])
+        ax = plt.subplots()[1]
+    ax.imshow(drawBoxes(image, predictions, boxes_format="predictions"))
     ax.set_xticks([])
-    for side, group in zip(["left", "right"], [left, right]):
-        for index, (text, box) in enumerate(group):
-            y = 1 - (index / len(group))
-            xy = box[0] / np.array([image.shape[1], image.shape[0]])
-            xy[1] = 1 - xy[1]
-            ax.annotate(text=text, xy=xy, xytext=(-0.05 if side == "left" else 1.05, y), xycoords="axes fraction",
-                        arrowprops={"arrowstyle": "->", "color": "r"}, color="r", fontsize=14,
+    ax.set_yticks([])
+    height, width = image.shape[:2]
+    columns = {"left": [], "right": []}
+    for word, quad in sorted(predictions, key=lambda item: item[1][:, 1].min()):
+        columns["left" if quad[:, 0].min() < width / 2 else "right"].append((word, quad))
+    for side, entries in columns.items():
+        for rank, (word, quad) in enumerate(entries):
+            anchor = (quad[0][0] / width, 1 - quad[0][1] / height)              # axes fraction, y upwards
+            label_at = (-0.05 if side == "left" else 1.05, 1 - rank / len(entries))
+            ax.annotate(text=word, xy=anchor, xytext=label_at, xycoords="axes fraction", color="r", fontsize=14,
+                        arrowprops={"arrowstyle": "->", "color": "r"},
                         horizontalalignment="right" if side == "left" else "left")
     return ax
