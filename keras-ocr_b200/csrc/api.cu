@@ -248,6 +248,7 @@ extern "C" int b2o_create(int device, b2o_ctx** out) {
   if (const char* e = getenv("B2O_TC_BOX_ALL")) ctx->tc_box_all = atoi(e) != 0;
   if (const char* e = getenv("B2O_UPCONV_COMMUTE")) ctx->no_commute = atoi(e) == 0;      // 1: commuted decoder upsampling (opt-in, see common.cuh)
   if (const char* e = getenv("B2O_TC_AFF")) ctx->tc_aff_const = std::string(e) != "smem";
+  if (const char* e = getenv("B2O_GLUE")) ctx->glue_v1 = std::string(e) == "v1";
   if (const char* e = getenv("B2O_FUSED_TAIL")) ctx->no_fused_tail = atoi(e) == 0;      // 0: separate head_tail_kernel (A/B, tests)
   if (const char* e = getenv("B2O_TC_PAIR")) {        // default 1; 0 = single-CTA tiles (A/B runs); 2 = generic tiles too
     ctx->tc_pair = atoi(e) != 0;

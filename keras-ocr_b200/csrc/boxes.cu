@@ -357,33 +357,45 @@ __device__ __forceinline__ uint32_t funnel_right(const uint32_t* row, int k, int
   return s == 0 ? cur : ((cur >> s) | (next << (32 - s)));
 }
 
-__global__ void __launch_bounds__(256)
-quads_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ label, int hs, int ws,
-             const Component* __restrict__ comps, const int* __restrict__ counts, int max_boxes,
-             float* __restrict__ boxes, uint32_t* __restrict__ big_planes, int* __restrict__ big_locks,
-             int smem_plane_words) {
-  extern __shared__ uint32_t dyn_smem[];
+// The dilation ROI of a component (detection.py:258-265) as a bit plane.
+struct Roi { int niter, sx, sy, rw, rh, stride, plane_words; };
+
+__device__ __forceinline__ Roi roi_of(const Component& c, int hs, int ws) {
+  Roi r;
+  // detection.py:258-260
+  const int mn = c.w < c.h ? c.w : c.h;
+  r.niter = static_cast<int>(sqrt(static_cast<double>(static_cast<long long>(c.area) * mn) /
+                                  static_cast<double>(static_cast<long long>(c.w) * c.h)) * 2.0);
+  r.sx = max(c.x - r.niter, 0); r.sy = max(c.y - r.niter, 0);
+  const int ex = min(c.x + c.w + r.niter + 1, ws), ey = min(c.y + c.h + r.niter + 1, hs);
+  r.rw = ex - r.sx; r.rh = ey - r.sy;
+  r.stride = (r.rw + 31) >> 5;
+  r.plane_words = r.stride * r.rh;
+  return r;
+}
+
+// Whether a component can be handled by the small-tile launch: both bit planes and the hull scratch that later
+// reuses plane B (worst case 2*rh hull points: 56 bytes per row + the padding of the index arrays) fit `words` words.
+__device__ __forceinline__ bool fits_words(const Roi& r, int words) {
+  return r.plane_words <= words && 56 * r.rh + 64 <= 4 * words;
+}
+
+// One component -> one quad.  `dyn_smem` holds two planes of `smem_plane_words` words; a component whose planes
+// do not fit works on the per-image global scratch planes instead (serialised by a per-image lock).
+__device__ void quad_of_component(const uint8_t* __restrict__ mask, const int* __restrict__ label, int hs, int ws,
+                                  const Component c, int img, float* __restrict__ out,
+                                  uint32_t* __restrict__ big_planes, int* __restrict__ big_locks,
+                                  uint32_t* dyn_smem, int smem_plane_words) {
   __shared__ int row_min[kMaxHullRows / 2], row_max[kMaxHullRows / 2];   // per blob row (<= 1024 rows)
   __shared__ int flag;
   __shared__ int first_word;
-  const int img = blockIdx.y, slot = blockIdx.x;
-  int cnt = counts[img];
-  if (cnt > max_boxes) cnt = max_boxes;
-  if (slot >= cnt) return;
-  const Component c = comps[static_cast<size_t>(img) * max_boxes + slot];
   const int hw = hs * ws;
   const uint8_t* M = mask + static_cast<size_t>(img) * hw;
   const int* L = label + static_cast<size_t>(img) * hw;
 
-  // detection.py:258-260
-  const int mn = c.w < c.h ? c.w : c.h;
-  const int niter = static_cast<int>(sqrt(static_cast<double>(static_cast<long long>(c.area) * mn) /
-                                          static_cast<double>(static_cast<long long>(c.w) * c.h)) * 2.0);
-  const int sx = max(c.x - niter, 0), sy = max(c.y - niter, 0);
-  const int ex = min(c.x + c.w + niter + 1, ws), ey = min(c.y + c.h + niter + 1, hs);
-  const int rw = ex - sx, rh = ey - sy;
-  const int stride = (rw + 31) >> 5;
-  const int plane_words = stride * rh;
+  const Roi roi = roi_of(c, hs, ws);
+  const int niter = roi.niter, sx = roi.sx, sy = roi.sy, rw = roi.rw, rh = roi.rh;
+  const int stride = roi.stride, plane_words = roi.plane_words;
   // cv2.dilate with a (1+niter)^2 rectangle, anchor k/2: a source pixel at j sets [j-(k-1-a), j+a]
   const int ksz = 1 + niter, grow_hi = ksz / 2, grow_lo = ksz - 1 - grow_hi;
 
@@ -400,21 +412,32 @@ quads_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ label, in
   }
 
   // plane B <- source mask S (component pixels minus text&link) ------------------------------
-  for (int i = threadIdx.x; i < plane_words; i += blockDim.x) {
-    const int ry = i / stride, k = i - ry * stride;
-    const int y = sy + ry;
-    uint32_t bits = 0;
-    if (y >= c.y && y < c.y + c.h) {
-      const int x0 = sx + 32 * k;
-      for (int b = 0; b < 32; ++b) {
-        const int x = x0 + b;
-        if (x >= c.x && x < c.x + c.w) {
-          const int q = y * ws + x;
-          if (L[q] == c.root && !(M[q] & 2)) bits |= (1u << b);
+  // one warp per word: lane b tests ROI column 32k + b (coalesced label / mask reads), the ballot is the word;
+  // four words per round so that their eight loads are in flight together
+  {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i0 = warp; i0 < plane_words; i0 += 4 * nwarps) {
+      bool bit[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int i = i0 + u * nwarps;
+        bit[u] = false;
+        if (i < plane_words) {
+          const int ry = i / stride, k = i - ry * stride;
+          const int y = sy + ry, x = sx + 32 * k + lane;
+          if (y >= c.y && y < c.y + c.h && x >= c.x && x < c.x + c.w) {
+            const int q = y * ws + x;
+            bit[u] = L[q] == c.root && !(M[q] & 2);
+          }
         }
       }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t bits = __ballot_sync(0xffffffffu, bit[u]);
+        const int i = i0 + u * nwarps;
+        if (lane == 0 && i < plane_words) B[i] = bits;
+      }
     }
-    B[i] = bits;
   }
   __syncthreads();
   // plane A <- horizontal dilation of B ------------------------------------------------------
@@ -493,7 +516,6 @@ quads_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ label, in
     __syncthreads();
   }
 
-  float* out = boxes + (static_cast<size_t>(img) * max_boxes + slot) * 8;
   if (!have_blob) {
     // The reference raises IndexError here (contours[0] of an empty list); we emit a NaN box.
     if (threadIdx.x < 8) out[threadIdx.x] = nanf("");
@@ -595,13 +617,53 @@ quads_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ label, in
   }
 }
 
+// Pass 1, one block of 128 threads per (box slot, image) with SMALL planes: eight blocks per SM instead of the two
+// that 96 KB planes allow (the work is a chain of short latency-bound phases, profiles/r2n_glue_full.csv: 17 % of
+// the warp slots active with the large planes).  Components that do not fit are queued for pass 2.
+__global__ void __launch_bounds__(256)
+quads_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ label, int hs, int ws,
+             const Component* __restrict__ comps, const int* __restrict__ counts, int max_boxes,
+             float* __restrict__ boxes, uint32_t* __restrict__ big_planes, int* __restrict__ big_locks,
+             int smem_plane_words, int* __restrict__ queue, int* __restrict__ queue_len) {
+  extern __shared__ uint32_t dyn_smem[];
+  const int img = blockIdx.y, slot = blockIdx.x;
+  int cnt = counts[img];
+  if (cnt > max_boxes) cnt = max_boxes;
+  if (slot >= cnt) return;
+  const size_t id = static_cast<size_t>(img) * max_boxes + slot;
+  const Component c = comps[id];
+  if (!fits_words(roi_of(c, hs, ws), smem_plane_words)) {
+    if (threadIdx.x == 0) queue[atomicAdd(queue_len, 1)] = static_cast<int>(id);
+    return;
+  }
+  quad_of_component(mask, label, hs, ws, c, img, boxes + id * 8, big_planes, big_locks, dyn_smem, smem_plane_words);
+}
+
+// Pass 2, a few blocks with the large planes walking the queue of pass 1 (normally empty).
+__global__ void __launch_bounds__(256)
+quads_queue_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ label, int hs, int ws,
+                   const Component* __restrict__ comps, int max_boxes, float* __restrict__ boxes,
+                   uint32_t* __restrict__ big_planes, int* __restrict__ big_locks, int smem_plane_words,
+                   const int* __restrict__ queue, const int* __restrict__ queue_len) {
+  extern __shared__ uint32_t dyn_smem[];
+  const int len = *queue_len;
+  for (int i = blockIdx.x; i < len; i += gridDim.x) {
+    const int id = queue[i];
+    quad_of_component(mask, label, hs, ws, comps[id], id / max_boxes, boxes + static_cast<size_t>(id) * 8, big_planes,
+                      big_locks, dyn_smem, smem_plane_words);
+    __syncthreads();       // thread 0 builds the hull in the planes' shared memory after the others have left
+  }
+}
+
 inline unsigned nblocks(long long total, int threads) { return static_cast<unsigned>((total + threads - 1) / threads); }
 inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
-constexpr int kQuadSmemPlaneWords = 12 * 1024;     // 2 planes x 48 KB: ROIs up to ~390k pixels stay in smem
+constexpr int kQuadSmemPlaneWords = 12 * 1024;     // pass 2: 2 planes x 48 KB, ROIs up to ~390k pixels stay in smem
+constexpr int kQuadSmallPlaneWords = 2 * 1024;     // pass 1: 2 planes x 8 KB, ROIs up to 65k pixels and 145 rows
 
 struct BoxWorkspace {
   uint8_t* mask; int* label; Stats st; Component* comps; uint32_t* big_planes; int* big_locks;
+  int* queue; int* queue_len;       // components that pass 1 of the quads leaves to pass 2
   size_t bytes;
 };
 
@@ -622,6 +684,8 @@ BoxWorkspace carve(void* ws, int n, int hs, int ws_w, int max_boxes) {
   w.comps = reinterpret_cast<Component*>(take(static_cast<size_t>(n) * max_boxes * sizeof(Component)));
   w.big_planes = reinterpret_cast<uint32_t*>(take(static_cast<size_t>(n) * 2 * ((ws_w + 31) / 32) * hs * 4));
   w.big_locks = reinterpret_cast<int*>(take(static_cast<size_t>(n) * 4));
+  w.queue = reinterpret_cast<int*>(take(static_cast<size_t>(n) * max_boxes * 4));
+  w.queue_len = reinterpret_cast<int*>(take(4));
   w.bytes = off;
   return w;
 }
@@ -657,6 +721,7 @@ extern "C" int b2o_get_boxes(b2o_ctx* ctx, const float* scores, int n, int hs, i
   B2O_CUDA_CHECK(ctx, cudaMemsetAsync(w.st.maxy, 0xff, px * 4, st));
   B2O_CUDA_CHECK(ctx, cudaMemsetAsync(w.st.maxtext, 0x80, px * 4, st));  // very negative key
   B2O_CUDA_CHECK(ctx, cudaMemsetAsync(w.big_locks, 0, static_cast<size_t>(n) * 4, st));
+  B2O_CUDA_CHECK(ctx, cudaMemsetAsync(w.queue_len, 0, 4, st));
   binarize_kernel<<<nblocks(total, 256), 256, 0, st>>>(scores, total, hs * ws, ws, text_threshold, link_threshold,
                                                       w.mask, w.label);
   B2O_LAUNCH_CHECK(ctx);
@@ -669,13 +734,19 @@ extern "C" int b2o_get_boxes(b2o_ctx* ctx, const float* scores, int n, int hs, i
   select_kernel<<<n, 1024, 0, st>>>(w.label, hs * ws, w.st, size_threshold, detection_threshold, w.comps, max_boxes,
                                     counts);
   B2O_LAUNCH_CHECK(ctx);
-  const int dyn = 2 * kQuadSmemPlaneWords * 4;
+  const int dyn = 2 * kQuadSmemPlaneWords * 4, dyn_small = 2 * kQuadSmallPlaneWords * 4;
   if (!ctx->quads_configured) {        // a per-device attribute, hence per context (one context per device)
-    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(quads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
+    B2O_CUDA_CHECK(ctx, cudaFuncSetAttribute(quads_queue_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn));
     ctx->quads_configured = true;
   }
-  quads_kernel<<<dim3(max_boxes, n), 256, dyn, st>>>(w.mask, w.label, hs, ws, w.comps, counts, max_boxes, boxes,
-                                                     w.big_planes, w.big_locks, kQuadSmemPlaneWords);
+  quads_kernel<<<dim3(max_boxes, n), 128, dyn_small, st>>>(w.mask, w.label, hs, ws, w.comps, counts, max_boxes, boxes,
+                                                           w.big_planes, w.big_locks, kQuadSmallPlaneWords, w.queue,
+                                                           w.queue_len);
+  B2O_LAUNCH_CHECK(ctx);
+  const long long slots = static_cast<long long>(n) * max_boxes;
+  quads_queue_kernel<<<static_cast<unsigned>(std::min<long long>(slots, 2 * ctx->sm_count)), 256, dyn, st>>>(
+      w.mask, w.label, hs, ws, w.comps, max_boxes, boxes, w.big_planes, w.big_locks, kQuadSmemPlaneWords, w.queue,
+      w.queue_len);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

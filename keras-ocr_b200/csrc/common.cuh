@@ -101,6 +101,7 @@ struct b2o_ctx {
   // gathers of the four taps are LSU-wavefront-bound.  Default: explicit UpsampleLike kernels.
   bool tc_aff_const = true;    // epilogue constants as a kernel parameter (constant cache); B2O_TC_AFF=smem: round-1 staging in shared memory / global loads
   bool no_commute = true;
+  bool glue_v1 = false;        // B2O_GLUE=v1: the round-1 upsample2x kernel (64-bit index chain, unshared blends) for A/B runs and the bit-identity test
   bool no_fused_tail = false;  // B2O_FUSED_TAIL=0: conv_cls.6/.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue
   std::set<const void*> configured;   // kernels whose per-device launch attributes are set on this device
   int64_t launches = 0;

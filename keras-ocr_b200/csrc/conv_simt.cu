@@ -274,26 +274,28 @@ __global__ void maxpool2_kernel(const __half* __restrict__ in, int in_ld, int N,
   *reinterpret_cast<uint4*>(out + static_cast<size_t>(op) * out_ld + cv * 8) = hmax8(hmax8(a, b), hmax8(c, d));
 }
 
-// 3x3 / stride 1 "same" max pool (padding never wins the max).
-__global__ void maxpool3s1_kernel(const __half* __restrict__ in, int in_ld, int N, int H, int W, int C,
-                                  __half* __restrict__ out, int out_ld) {
-  const int CV = C / 8;
-  const long long total = static_cast<long long>(N) * H * W * CV;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = static_cast<int>(idx % CV);
-  const long long op = idx / CV;
-  const int w = static_cast<int>(op % W);
-  const int h = static_cast<int>((op / W) % H);
-  const int n = static_cast<int>(op / (static_cast<long long>(W) * H));
-  uint4 m = *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(n) * H + h) * W + w) * in_ld + cv * 8);
-  for (int dy = -1; dy <= 1; ++dy)
-    for (int dx = -1; dx <= 1; ++dx) {
-      const int ih = h + dy, iw = w + dx;
-      if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-      m = hmax8(m, *reinterpret_cast<const uint4*>(in + ((static_cast<size_t>(n) * H + ih) * W + iw) * in_ld + cv * 8));
-    }
-  *reinterpret_cast<uint4*>(out + static_cast<size_t>(op) * out_ld + cv * 8) = m;
+// 3x3 / stride 1 "same" max pool (padding never wins the max).  blockIdx.y walks the images so that the index
+// inside one image fits 32 bits (64-bit div/mod was most of this kernel's instructions).
+__global__ void __launch_bounds__(256, 4)
+maxpool3s1_kernel(const __half* __restrict__ in, int in_ld, int N, int H, int W, int C, __half* __restrict__ out,
+                  int out_ld) {
+  const unsigned CV = C / 8;
+  const unsigned per_image = static_cast<unsigned>(H) * W * CV;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= per_image) return;
+  const unsigned cv = idx % CV, op = idx / CV;
+  const int w = static_cast<int>(op % W), h = static_cast<int>(op / W);
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    const __half* src = in + static_cast<size_t>(n) * H * W * in_ld + cv * 8;
+    uint4 m = *reinterpret_cast<const uint4*>(src + (static_cast<size_t>(h) * W + w) * in_ld);
+    for (int dy = -1; dy <= 1; ++dy)
+      for (int dx = -1; dx <= 1; ++dx) {
+        const int ih = h + dy, iw = w + dx;
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+        m = hmax8(m, *reinterpret_cast<const uint4*>(src + (static_cast<size_t>(ih) * W + iw) * in_ld));
+      }
+    *reinterpret_cast<uint4*>(out + (static_cast<size_t>(n) * H * W + op) * out_ld + cv * 8) = m;
+  }
 }
 
 // Bilinear resize with half-pixel centres (tf resize_bilinear(half_pixel_centers=True) ==
@@ -345,7 +347,7 @@ __global__ void upsample_kernel(const __half* __restrict__ in, int in_ld, int N,
 // from ONE set of four loads.  Weights are those of upsample_kernel (0.25 / 0.75, and 0 on the first
 // row/column where the source coordinate clamps to 0), and the expression has the same form, so both
 // kernels give identical bits.
-__global__ void upsample2x_kernel(const __half* __restrict__ in, int in_ld, int N, int IH, int IW, int C,
+__global__ void upsample2x_v1_kernel(const __half* __restrict__ in, int in_ld, int N, int IH, int IW, int C,
                                   __half* __restrict__ out, int out_ld) {
   const int CV = C / 8;
   const int QW = IW + 1, QH = IH + 1;
@@ -390,6 +392,67 @@ __global__ void upsample2x_kernel(const __half* __restrict__ in, int in_ld, int 
         pr[i] = __floats2half2_rn(vx, vy);
       }
       *reinterpret_cast<uint4*>(out + ((static_cast<size_t>(n) * OH + oh) * OW + ow) * out_ld + cv * 8) = r;
+    }
+  }
+}
+
+// The same quads with a third of the instructions (the v1 kernel issues 650 per thread and is issue-bound at 3.5 TB/s,
+// profiles/r2n_glue_full.csv): blockIdx.y walks the images so the decomposition of the index is 32-bit, and the two
+// horizontal blends of a quad column (rows ya and yb) are formed once and shared by its two output rows.  Every
+// product and sum is the one v1 forms (same operands, same association), so the bits are v1's (B2O_GLUE=v1 A/B test).
+__global__ void __launch_bounds__(256, 4)
+upsample2x_kernel(const __half* __restrict__ in, int in_ld, int N, int IH, int IW, int C, __half* __restrict__ out,
+                  int out_ld) {
+  const unsigned CV = C / 8;
+  const unsigned QW = IW + 1, QH = IH + 1;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= QH * QW * CV) return;
+  const unsigned cv = idx % CV, q = idx / CV;
+  const int qx = static_cast<int>(q % QW), qy = static_cast<int>(q / QW);
+  const int ya = max(qy - 1, 0), yb = min(qy, IH - 1);
+  const int xa = max(qx - 1, 0), xb = min(qx, IW - 1);
+  const int OH = 2 * IH, OW = 2 * IW;
+  const int oh0 = 2 * qy - 1, ow0 = 2 * qx - 1;
+  for (int n = blockIdx.y; n < N; n += gridDim.y) {
+    const __half* base = in + static_cast<size_t>(n) * IH * IW * in_ld + cv * 8;
+    const uint4 a = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(ya) * IW + xa) * in_ld);
+    const uint4 b = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(ya) * IW + xb) * in_ld);
+    const uint4 c = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(yb) * IW + xa) * in_ld);
+    const uint4 d = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(yb) * IW + xb) * in_ld);
+    float fa[8], fb[8], fc[8], fd[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 va = __half22float2(reinterpret_cast<const __half2*>(&a)[i]);
+      const float2 vb = __half22float2(reinterpret_cast<const __half2*>(&b)[i]);
+      const float2 vc = __half22float2(reinterpret_cast<const __half2*>(&c)[i]);
+      const float2 vd = __half22float2(reinterpret_cast<const __half2*>(&d)[i]);
+      fa[2 * i] = va.x; fa[2 * i + 1] = va.y; fb[2 * i] = vb.x; fb[2 * i + 1] = vb.y;
+      fc[2 * i] = vc.x; fc[2 * i + 1] = vc.y; fd[2 * i] = vd.x; fd[2 * i + 1] = vd.y;
+    }
+    __half* obase = out + static_cast<size_t>(n) * OH * OW * out_ld + cv * 8;
+#pragma unroll
+    for (int rx = 0; rx < 2; ++rx) {
+      const int ow = ow0 + rx;
+      if (ow < 0 || ow >= OW) continue;
+      const float lx = rx == 0 ? 0.25f : (qx == 0 ? 0.0f : 0.75f), hx = 1.0f - lx;
+      float top[8], bot[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        top[i] = hx * fa[i] + lx * fb[i];
+        bot[i] = hx * fc[i] + lx * fd[i];
+      }
+#pragma unroll
+      for (int ry = 0; ry < 2; ++ry) {
+        const int oh = oh0 + ry;
+        if (oh < 0 || oh >= OH) continue;
+        const float ly = ry == 0 ? 0.25f : (qy == 0 ? 0.0f : 0.75f), hy = 1.0f - ly;
+        uint4 r;
+        __half2* pr = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          pr[i] = __floats2half2_rn(hy * top[2 * i] + ly * bot[2 * i], hy * top[2 * i + 1] + ly * bot[2 * i + 1]);
+        *reinterpret_cast<uint4*>(obase + (static_cast<size_t>(oh) * OW + ow) * out_ld) = r;
+      }
     }
   }
 }
@@ -502,16 +565,24 @@ int maxpool2_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cuda
 }
 
 int maxpool3s1_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cudaStream_t st) {
-  const long long total = static_cast<long long>(in.n) * in.h * in.w * (in.c / 8);
-  maxpool3s1_kernel<<<blocks_for(total, 256), 256, 0, st>>>(in.ptr, in.ld, in.n, in.h, in.w, in.c, out.ptr, out.ld);
+  const long long per_image = static_cast<long long>(in.h) * in.w * (in.c / 8);
+  if (per_image == 0 || in.n == 0) return B2O_OK;
+  maxpool3s1_kernel<<<dim3(blocks_for(per_image, 256), std::min(in.n, 65535)), 256, 0, st>>>(
+      in.ptr, in.ld, in.n, in.h, in.w, in.c, out.ptr, out.ld);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }
 
 int upsample_run(b2o_ctx* ctx, const TensorView& in, const TensorView& out, cudaStream_t st) {
+  if (in.n == 0 || out.h == 0 || out.w == 0) return B2O_OK;
   if (out.h == 2 * in.h && out.w == 2 * in.w) {
-    const long long quads = static_cast<long long>(in.n) * (in.h + 1) * (in.w + 1) * (in.c / 8);
-    upsample2x_kernel<<<blocks_for(quads, 256), 256, 0, st>>>(in.ptr, in.ld, in.n, in.h, in.w, in.c, out.ptr, out.ld);
+    const long long per_image = static_cast<long long>(in.h + 1) * (in.w + 1) * (in.c / 8);
+    if (ctx->glue_v1)
+      upsample2x_v1_kernel<<<blocks_for(per_image * in.n, 256), 256, 0, st>>>(in.ptr, in.ld, in.n, in.h, in.w, in.c,
+                                                                            out.ptr, out.ld);
+    else
+      upsample2x_kernel<<<dim3(blocks_for(per_image, 256), std::min(in.n, 65535)), 256, 0, st>>>(
+          in.ptr, in.ld, in.n, in.h, in.w, in.c, out.ptr, out.ld);
     B2O_LAUNCH_CHECK(ctx);
     return B2O_OK;
   }

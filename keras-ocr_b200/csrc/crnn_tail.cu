@@ -32,49 +32,49 @@ __device__ __forceinline__ float linspace_pm1(int i, int n) {
 // feat/out: (B, Hh, Ww, C) fp16 with Hh = 50 ("height" of the STN, the time axis), Ww = 7.
 __global__ void stn_sample_kernel(const __half* __restrict__ feat, const float* __restrict__ theta, int B, int Hh,
                                   int Ww, int C, __half* __restrict__ out) {
-  const int CV = C / 8;
-  const long long total = static_cast<long long>(B) * Hh * Ww * CV;
-  const long long idx = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int cv = static_cast<int>(idx % CV);
-  const long long pp = idx / CV;
-  const int ix = static_cast<int>(pp % Ww);
-  const int iy = static_cast<int>((pp / Ww) % Hh);
-  const int b = static_cast<int>(pp / (static_cast<long long>(Ww) * Hh));
-  const float* th = theta + b * 6;
-  const float gx = linspace_pm1(ix, Ww), gy = linspace_pm1(iy, Hh);
-  const float xs = __fadd_rn(__fadd_rn(__fmul_rn(th[0], gx), __fmul_rn(th[1], gy)), th[2]);
-  const float ys = __fadd_rn(__fadd_rn(__fmul_rn(th[3], gx), __fmul_rn(th[4], gy)), th[5]);
-  const float x = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(xs, 1.0f)), static_cast<float>(Ww));
-  const float y = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(ys, 1.0f)), static_cast<float>(Hh));
-  // floor -> int32 cast like tf.cast(tf.floor(x), "int32"); clamp the float first so the cast is defined
-  int x0 = static_cast<int>(floorf(fminf(fmaxf(x, -1.0e6f), 1.0e6f)));
-  int y0 = static_cast<int>(floorf(fminf(fmaxf(y, -1.0e6f), 1.0e6f)));
-  int x1 = x0 + 1, y1 = y0 + 1;
-  x0 = min(max(x0, 0), Ww - 1); x1 = min(max(x1, 0), Ww - 1);
-  y0 = min(max(y0, 0), Hh - 1); y1 = min(max(y1, 0), Hh - 1);
-  const float fx0 = static_cast<float>(x0), fx1 = static_cast<float>(x1);
-  const float fy0 = static_cast<float>(y0), fy1 = static_cast<float>(y1);
-  const float wa = __fmul_rn(fx1 - x, fy1 - y), wb = __fmul_rn(fx1 - x, y - fy0);
-  const float wc = __fmul_rn(x - fx0, fy1 - y), wd = __fmul_rn(x - fx0, y - fy0);
-  const __half* base = feat + static_cast<size_t>(b) * Hh * Ww * C + cv * 8;
-  const uint4 ra = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * Ww + x0) * C);
-  const uint4 rb = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * Ww + x0) * C);
-  const uint4 rc = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * Ww + x1) * C);
-  const uint4 rd = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * Ww + x1) * C);
-  const __half2* pa = reinterpret_cast<const __half2*>(&ra);
-  const __half2* pb = reinterpret_cast<const __half2*>(&rb);
-  const __half2* pc = reinterpret_cast<const __half2*>(&rc);
-  const __half2* pd = reinterpret_cast<const __half2*>(&rd);
-  uint4 r;
-  __half2* pr = reinterpret_cast<__half2*>(&r);
+  // blockIdx.y walks the crops: the index inside one crop is 32-bit (the 64-bit div/mod chain was most of the kernel)
+  const unsigned CV = C / 8;
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<unsigned>(Hh) * Ww * CV) return;
+  const unsigned cv = idx % CV, pix = idx / CV;
+  const int ix = static_cast<int>(pix % Ww), iy = static_cast<int>(pix / Ww);
+  for (int b = blockIdx.y; b < B; b += gridDim.y) {
+    const long long pp = static_cast<long long>(b) * Hh * Ww + pix;
+    const float* th = theta + b * 6;
+    const float gx = linspace_pm1(ix, Ww), gy = linspace_pm1(iy, Hh);
+    const float xs = __fadd_rn(__fadd_rn(__fmul_rn(th[0], gx), __fmul_rn(th[1], gy)), th[2]);
+    const float ys = __fadd_rn(__fadd_rn(__fmul_rn(th[3], gx), __fmul_rn(th[4], gy)), th[5]);
+    const float x = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(xs, 1.0f)), static_cast<float>(Ww));
+    const float y = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(ys, 1.0f)), static_cast<float>(Hh));
+    // floor -> int32 cast like tf.cast(tf.floor(x), "int32"); clamp the float first so the cast is defined
+    int x0 = static_cast<int>(floorf(fminf(fmaxf(x, -1.0e6f), 1.0e6f)));
+    int y0 = static_cast<int>(floorf(fminf(fmaxf(y, -1.0e6f), 1.0e6f)));
+    int x1 = x0 + 1, y1 = y0 + 1;
+    x0 = min(max(x0, 0), Ww - 1); x1 = min(max(x1, 0), Ww - 1);
+    y0 = min(max(y0, 0), Hh - 1); y1 = min(max(y1, 0), Hh - 1);
+    const float fx0 = static_cast<float>(x0), fx1 = static_cast<float>(x1);
+    const float fy0 = static_cast<float>(y0), fy1 = static_cast<float>(y1);
+    const float wa = __fmul_rn(fx1 - x, fy1 - y), wb = __fmul_rn(fx1 - x, y - fy0);
+    const float wc = __fmul_rn(x - fx0, fy1 - y), wd = __fmul_rn(x - fx0, y - fy0);
+    const __half* base = feat + static_cast<size_t>(b) * Hh * Ww * C + cv * 8;
+    const uint4 ra = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * Ww + x0) * C);
+    const uint4 rb = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * Ww + x0) * C);
+    const uint4 rc = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y0) * Ww + x1) * C);
+    const uint4 rd = *reinterpret_cast<const uint4*>(base + (static_cast<size_t>(y1) * Ww + x1) * C);
+    const __half2* pa = reinterpret_cast<const __half2*>(&ra);
+    const __half2* pb = reinterpret_cast<const __half2*>(&rb);
+    const __half2* pc = reinterpret_cast<const __half2*>(&rc);
+    const __half2* pd = reinterpret_cast<const __half2*>(&rd);
+    uint4 r;
+    __half2* pr = reinterpret_cast<__half2*>(&r);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 a = __half22float2(pa[i]), bb = __half22float2(pb[i]);
-    const float2 c = __half22float2(pc[i]), d = __half22float2(pd[i]);
-    pr[i] = __floats2half2_rn(wa * a.x + wb * bb.x + wc * c.x + wd * d.x, wa * a.y + wb * bb.y + wc * c.y + wd * d.y);
+    for (int i = 0; i < 4; ++i) {
+      const float2 a = __half22float2(pa[i]), bb = __half22float2(pb[i]);
+      const float2 c = __half22float2(pc[i]), d = __half22float2(pd[i]);
+      pr[i] = __floats2half2_rn(wa * a.x + wb * bb.x + wc * c.x + wd * d.x, wa * a.y + wb * bb.y + wc * c.y + wd * d.y);
+    }
+    *reinterpret_cast<uint4*>(out + static_cast<size_t>(pp) * C + cv * 8) = r;
   }
-  *reinterpret_cast<uint4*>(out + static_cast<size_t>(pp) * C + cv * 8) = r;
 }
 
 // ---------------------------------------------------------------------------------------- STN conv_a tail
@@ -310,8 +310,8 @@ int stn_col2im_run(b2o_ctx* ctx, const __half* y, const float* bias, int B, __ha
 }
 
 int stn_sample_run(b2o_ctx* ctx, const __half* feat, const float* theta, int B, __half* out, cudaStream_t st) {
-  const long long total = static_cast<long long>(B) * 50 * 7 * (512 / 8);
-  stn_sample_kernel<<<nb(total, 256), 256, 0, st>>>(feat, theta, B, 50, 7, 512, out);
+  if (B <= 0) return B2O_OK;
+  stn_sample_kernel<<<dim3(nb(50 * 7 * (512 / 8), 256), B < 65535 ? B : 65535), 256, 0, st>>>(feat, theta, B, 50, 7, 512, out);
   B2O_LAUNCH_CHECK(ctx);
   return B2O_OK;
 }

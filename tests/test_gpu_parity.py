@@ -190,7 +190,17 @@ def test_get_boxes_vs_oracle_large_and_adversarial(detector):
     adv[0, 100:130, 40:70, 0] = 0.85                    # square blob -> "diamond" branch (276-281)
     yy, xx = np.mgrid[0:160, 0:200]
     adv[0, ..., 0] = np.maximum(adv[0, ..., 0], 0.9 * (np.abs(yy - 120) + np.abs(xx - 150) < 18))   # rotated square
-    for scores in (maps, adv):
+    # components beyond the small shared-memory planes of the quads' first pass: two text blocks whose dilation
+    # ROI (973 x 403) exceeds even the large planes (global scratch planes, both in one image: the per-image lock),
+    # one of them with its middle removed as text & link, a 195-row block (second pass, large shared-memory planes),
+    # and an ordinary word next to them
+    big = np.zeros((1, 1000, 1000, 2), np.float32)
+    big[0, 10:340, 50:950, 0] = 0.9
+    big[0, 420:750, 40:940, 0] = 0.85
+    big[0, 500:600, 300:500, 1] = 0.9
+    big[0, 830:990, 100:400, 0] = 0.9
+    big[0, 900:910, 500:560, 0] = 0.8
+    for scores in (maps, adv, big):
         _check_boxes(detector, scores, imageops.get_boxes(scores))
 
 
@@ -856,9 +866,9 @@ def test_decoder_commute_matches_explicit_upsample(cuda_device, monkeypatch, gol
 
 
 @pytest.mark.parametrize("switch", [("B2O_TC_BOX16", "0"), ("B2O_TC_BOX16", "10"), ("B2O_TC_BOX16", "16"), ("B2O_TC_BOX_ALL", "1"), ("B2O_TC_PAIR", "2"),
-                                    ("B2O_FUSED_TAIL", "0"), ("B2O_TC_AFF", "smem")],
+                                    ("B2O_FUSED_TAIL", "0"), ("B2O_TC_AFF", "smem"), ("B2O_GLUE", "v1")],
                          ids=["three_boxes_vs_single_box", "box_width_10", "box_width_16", "single_box_everywhere", "generic_pairs", "separate_head_tail",
-                              "epilogue_constants_in_smem"])
+                              "epilogue_constants_in_smem", "round1_upsample2x"])
 def test_conv_variants_are_bit_identical(cuda_device, monkeypatch, switch):
     """Kernel variants that keep the MMA / fmaf order of the default path must not change a bit of the CRAFT score
     maps or the CRNN logits:  B2O_TC_BOX16=0 -- three 8 x 18 A boxes per K chunk instead of the default single
@@ -866,7 +876,8 @@ def test_conv_variants_are_bit_identical(cuda_device, monkeypatch, switch):
     a swizzle atom), B2O_TC_BOX_ALL=1 -- single boxes in every grouped layer;  B2O_TC_PAIR=2 -- CTA pairs on the generic tiles too;
     B2O_FUSED_TAIL=0 -- conv_cls.6 / conv_cls.8 as the separate head_tail_kernel instead of conv_cls.4's epilogue;
     B2O_TC_AFF=smem -- the per-channel epilogue constants staged in shared memory / read from global memory (round 1)
-    instead of the kernel-parameter constant bank.
+    instead of the kernel-parameter constant bank;  B2O_GLUE=v1 -- the round-1 2x upsampling kernel (64-bit index chain, each output
+    pixel blending its four taps on its own) instead of the one that shares a quad column's two horizontal blends.
     Sizes: odd tile columns (200 / 8 = 25), several tiles per CTA, and the 768 x 768 case of BASELINE configs[1]."""
     from keras_ocr_b200.detection import Detector
     from keras_ocr_b200.recognition import Recognizer
