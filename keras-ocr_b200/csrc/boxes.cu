@@ -387,7 +387,6 @@ __device__ void quad_of_component(const uint8_t* __restrict__ mask, const int* _
                                   uint32_t* __restrict__ big_planes, int* __restrict__ big_locks,
                                   uint32_t* dyn_smem, int smem_plane_words) {
   __shared__ int row_min[kMaxHullRows / 2], row_max[kMaxHullRows / 2];   // per blob row (<= 1024 rows)
-  __shared__ int flag;
   __shared__ int first_word;
   const int hw = hs * ws;
   const uint8_t* M = mask + static_cast<size_t>(img) * hw;
@@ -412,30 +411,29 @@ __device__ void quad_of_component(const uint8_t* __restrict__ mask, const int* _
   }
 
   // plane B <- source mask S (component pixels minus text&link) ------------------------------
-  // one warp per word: lane b tests ROI column 32k + b (coalesced label / mask reads), the ballot is the word;
-  // four words per round so that their eight loads are in flight together
+  // one warp per ROI row, lane b tests column 32k + b of the row's word k (coalesced label / mask reads), the ballot
+  // is the word; four words per round so that their eight loads are in flight together
   {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int i0 = warp; i0 < plane_words; i0 += 4 * nwarps) {
-      bool bit[4];
+    for (int ry = warp; ry < rh; ry += nwarps) {
+      const int y = sy + ry;
+      const bool row_in = y >= c.y && y < c.y + c.h;
+      for (int k0 = 0; k0 < stride; k0 += 4) {
+        bool bit[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int i = i0 + u * nwarps;
-        bit[u] = false;
-        if (i < plane_words) {
-          const int ry = i / stride, k = i - ry * stride;
-          const int y = sy + ry, x = sx + 32 * k + lane;
-          if (y >= c.y && y < c.y + c.h && x >= c.x && x < c.x + c.w) {
+        for (int u = 0; u < 4; ++u) {
+          const int x = sx + 32 * (k0 + u) + lane;
+          bit[u] = false;
+          if (row_in && k0 + u < stride && x >= c.x && x < c.x + c.w) {
             const int q = y * ws + x;
             bit[u] = L[q] == c.root && !(M[q] & 2);
           }
         }
-      }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const uint32_t bits = __ballot_sync(0xffffffffu, bit[u]);
-        const int i = i0 + u * nwarps;
-        if (lane == 0 && i < plane_words) B[i] = bits;
+        for (int u = 0; u < 4; ++u) {
+          const uint32_t bits = __ballot_sync(0xffffffffu, bit[u]);
+          if (lane == 0 && k0 + u < stride) B[ry * stride + k0 + u] = bits;
+        }
       }
     }
   }
@@ -484,34 +482,52 @@ __device__ void quad_of_component(const uint8_t* __restrict__ mask, const int* _
     __syncthreads();
     if (threadIdx.x == 0) A[fw] = B[fw] & (0u - B[fw]);           // lowest set bit = first pixel
     __syncthreads();
-    while (true) {
-      if (threadIdx.x == 0) flag = 0;
-      __syncthreads();
-      for (int i = threadIdx.x; i < plane_words; i += blockDim.x) {
-        const uint32_t d = B[i];
-        if (!d) continue;
-        const int ry = i / stride, k = i - ry * stride;
-        uint32_t nb = 0;
-        for (int dr = -1; dr <= 1; ++dr) {
-          const int r = ry + dr;
-          if (r < 0 || r >= rh) continue;
-          const uint32_t* row = A + r * stride;
-          const uint32_t cur = row[k];
-          const uint32_t prev = k > 0 ? row[k - 1] : 0u;
-          const uint32_t next = (k + 1 < stride) ? row[k + 1] : 0u;
-          nb |= cur | (cur << 1) | (cur >> 1) | (prev >> 31) | (next << 31);
+    // Close A under "8-neighbour inside B" with ONE warp sweeping the rows, alternately downwards and upwards, lane =
+    // word of the row: a sweep carries the fill through every row it passes, so a blob takes about three sweeps
+    // (down, up, one that changes nothing) where the all-words-at-once iteration took one round per row of the blob
+    // -- 64 rounds over ~480 words on the bench pages, half of this kernel's instructions (profiles/r2o_quads_source.txt).
+    // The result is the same set: the smallest one that contains the seed and is closed under that neighbourhood.
+    if (threadIdx.x < 32) {
+      const int lane = threadIdx.x;
+      bool down = true;
+      while (true) {
+        bool changed = false;
+        for (int rr = 0; rr < rh; ++rr) {
+          const int r = down ? rr : rh - 1 - rr;
+          for (int k0 = 0; k0 < stride; k0 += 32) {
+            const int k = k0 + lane;
+            uint32_t cur = 0, grown = 0;
+            if (k < stride) {
+              const uint32_t d = B[r * stride + k];
+              if (d) {
+                uint32_t nb = 0;
+                for (int dr = -1; dr <= 1; ++dr) {
+                  const int r2 = r + dr;
+                  if (r2 < 0 || r2 >= rh) continue;
+                  const uint32_t* row = A + r2 * stride;
+                  const uint32_t mid = row[k];
+                  const uint32_t prev = k > 0 ? row[k - 1] : 0u;
+                  const uint32_t next = (k + 1 < stride) ? row[k + 1] : 0u;
+                  if (dr == 0) cur = mid;
+                  nb |= mid | (mid << 1) | (mid >> 1) | (prev >> 31) | (next << 31);
+                }
+                grown = nb & d;
+                // finish the fill along the row inside this word (runs of d reachable from grown)
+                uint32_t prevg;
+                do { prevg = grown; grown |= ((grown << 1) | (grown >> 1)) & d; } while (grown != prevg);
+                grown &= ~cur;
+              }
+            }
+            __syncwarp();                                   // every lane has read row r before any lane writes it
+            if (grown) { A[r * stride + k] = cur | grown; changed = true; }
+            __syncwarp();
+          }
         }
-        uint32_t grown = nb & d;
-        // finish the fill along the row inside this word (runs of d reachable from grown)
-        uint32_t prevg;
-        do { prevg = grown; grown |= ((grown << 1) | (grown >> 1)) & d; } while (grown != prevg);
-        if (grown & ~A[i]) { atomicOr(&A[i], grown); flag = 1; }
+        if (!__any_sync(0xffffffffu, changed)) break;       // a whole sweep without a change: closed
+        down = !down;
       }
-      __syncthreads();
-      const int again = flag;
-      __syncthreads();
-      if (!again) break;
     }
+    __syncthreads();
     for (int i = threadIdx.x; i < plane_words; i += blockDim.x) B[i] &= ~A[i];
     __syncthreads();
   }
