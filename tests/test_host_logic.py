@@ -81,3 +81,76 @@ def test_keras_h5_dataset_mapping_round_trip():
         W.map_keras_datasets({"model_1/conv2d_8/kernel:0": np.zeros((3, 3, 8, 8), np.float32)})
     with pytest.raises(FileNotFoundError):
         W.load_keras_h5("/nonexistent/crnn_kurapan.h5")
+
+
+# ------------------------------------------------------------------- box geometry of warpBox (host side, tools.py:41-57, 533-581)
+def _rect_area(r):
+    return float(np.linalg.norm(r[1] - r[0]) * np.linalg.norm(r[2] - r[1]))
+
+
+def test_minimum_rotated_rectangle_properties_and_cv2_area():
+    """shapely is not installable offline, so the restated ``minimum_rotated_rectangle`` is checked through what defines it:
+    a rectangle, containing every point, one side on a hull edge, and of the least area -- the area against
+    cv2.minAreaRect (rotating calipers, an independent implementation) and against the oracle's own restatement."""
+    import cv2
+    from keras_ocr_b200 import tools
+    from oracle import imageops
+    rng = np.random.default_rng(11)
+    for trial in range(200):
+        n = int(rng.integers(3, 9))
+        pts = rng.uniform(0, 300, (n, 2)) if trial % 3 else rng.integers(0, 40, (n, 2)).astype(np.float64)
+        rect = tools.minimum_rotated_rectangle(pts)
+        hull = tools._convex_hull(pts)
+        if len(hull) < 3:
+            assert rect is None and imageops.min_rotated_rectangle(pts) is None
+            continue
+        sides = np.roll(rect, -1, 0) - rect
+        for i in range(4):                                   # right angles, opposite sides equal
+            assert abs(np.dot(sides[i], sides[(i + 1) % 4])) <= 1e-6 * max(1.0, _rect_area(rect))
+        assert np.allclose(sides[0], -sides[2], atol=1e-8) and np.allclose(sides[1], -sides[3], atol=1e-8)
+        u, v = sides[0] / np.linalg.norm(sides[0]), sides[1] / np.linalg.norm(sides[1])
+        a, b = (pts - rect[0]) @ u, (pts - rect[0]) @ v      # every point inside
+        assert a.min() >= -1e-7 and a.max() <= np.linalg.norm(sides[0]) + 1e-7
+        assert b.min() >= -1e-7 and b.max() <= np.linalg.norm(sides[1]) + 1e-7
+        edges = np.roll(hull, -1, 0) - hull                  # one side lies along a hull edge
+        cosines = np.abs(edges @ u) / np.linalg.norm(edges, axis=1)
+        assert (np.minimum(np.abs(cosines - 1.0), np.abs(cosines)) <= 1e-9).any()
+        (_, (cw, ch), _) = cv2.minAreaRect(pts.astype(np.float32))
+        assert abs(_rect_area(rect) - cw * ch) <= 2e-4 * max(cw * ch, 1.0), (trial, _rect_area(rect), cw * ch)
+        np.testing.assert_allclose(rect, imageops.min_rotated_rectangle(pts), atol=1e-9)
+
+
+def test_get_rotated_box_orders_corners_like_the_reference():
+    """tools.get_rotated_box (reference tools.py:533-581): top-left, top-right, bottom-right, bottom-left for an upright and
+    a tilted rectangle whatever the order of the input corners; width / height as get_rotated_width_height (41-57)."""
+    from keras_ocr_b200 import tools
+    from oracle import imageops
+    upright = np.array([[10, 20], [110, 20], [110, 50], [10, 50]], np.float32)
+    c, s = np.cos(0.3), np.sin(0.3)
+    tilted = (upright - upright.mean(0)) @ np.array([[c, s], [-s, c]], np.float32) + upright.mean(0)
+    rng = np.random.default_rng(3)
+    for quad in (upright, tilted.astype(np.float32)):
+        for _ in range(8):
+            box, _rot = tools.get_rotated_box(quad[rng.permutation(4)])
+            np.testing.assert_allclose(box, quad, atol=2e-4)
+            np.testing.assert_array_equal(box, imageops.order_corners(box))
+            wh = tools.get_rotated_width_height(box)
+            assert wh == imageops.rotated_width_height(box)
+            assert wh[0] in (99, 100) and wh[1] in (29, 30)      # int() truncates the fp32-rounded side lengths
+
+
+def test_rectify_boxes_keeps_rectangles_replaces_quads_and_raises_on_degenerate_boxes():
+    from keras_ocr_b200 import tools
+    rect = np.array([[10, 20], [110, 20], [110, 50], [10, 50]], np.float32)
+    c, s = np.cos(-0.2), np.sin(-0.2)
+    tilted = ((rect - rect.mean(0)) @ np.array([[c, s], [-s, c]], np.float32) + rect.mean(0)).astype(np.float32)
+    trapezoid = np.array([[10, 20], [110, 25], [100, 60], [20, 50]], np.float32)
+    out = tools.rectify_boxes(np.stack([rect, tilted, trapezoid]))
+    np.testing.assert_array_equal(out[0], rect)              # rectangles: bit for bit (everything getBoxes emits)
+    np.testing.assert_array_equal(out[1], tilted)
+    assert np.abs(out[2] - trapezoid).max() > 1.0            # a general quad becomes its minimum rotated rectangle ...
+    np.testing.assert_allclose(out[2], tools.get_rotated_box(trapezoid)[0])
+    sides = np.roll(out[2], -1, 0) - out[2]
+    assert abs(float(np.dot(sides[0], sides[1]))) <= 1e-2    # ... which is a rectangle
+    with pytest.raises(ZeroDivisionError):                   # tools.py:95: scale = min(target_width / w, target_height / h)
+        tools.rectify_boxes(np.array([[[5, 5], [5.4, 5], [5.4, 30], [5, 30]]], np.float32))
